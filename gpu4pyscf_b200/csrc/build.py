@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Build libgvhf_rys_b200.so for sm_100a (nvcc), in-tree.
+
+    python -m gpu4pyscf_b200.csrc.build            # CUDA library -> gpu4pyscf_b200/lib/
+    python -m gpu4pyscf_b200.csrc.build --emul     # CPU SIMT emulation (tests only) -> tests/emul/
+
+Only the standard toolchain is used (nvcc / g++); objects are cached under
+gpu4pyscf_b200/csrc/build/ and rebuilt when a source or header is newer.
+"""
+import os
+import sys
+import glob
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+
+def _generate():
+    gen = os.path.join(HERE, 'gen')
+    script = os.path.join(ROOT, 'tools', 'gen_instances.py')
+    stamp = os.path.join(gen, 'jk_dispatch.inc')
+    if not os.path.exists(stamp) or os.path.getmtime(stamp) < os.path.getmtime(script):
+        subprocess.check_call([sys.executable, script, gen], stdout=subprocess.DEVNULL)
+    return sorted(glob.glob(os.path.join(gen, 'jk_inst_*.cu')))
+
+
+def _newest_header():
+    hs = glob.glob(os.path.join(HERE, '*.cuh')) + glob.glob(os.path.join(HERE, '*.h')) \
+        + glob.glob(os.path.join(HERE, 'gen', '*.inc'))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def build(emul=False, verbose=False, jobs=None):
+    srcs = _generate() + [os.path.join(HERE, 'capi.cu')]
+    tag = 'emul' if emul else 'sm100a'
+    objdir = os.path.join(HERE, 'build', tag)
+    os.makedirs(objdir, exist_ok=True)
+    if emul:
+        shim = os.path.join(ROOT, 'tests', 'emul')
+        srcs = srcs + [os.path.join(shim, 'cuda_shim.cpp')]
+        out = os.path.join(shim, 'libgvhf_rys_b200_emul.so')
+        hdr_time = max(_newest_header(), os.path.getmtime(os.path.join(shim, 'cuda_shim.h')))
+    else:
+        out = os.path.join(ROOT, 'gpu4pyscf_b200', 'lib', 'libgvhf_rys_b200.so')
+        hdr_time = _newest_header()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src).rsplit('.', 1)[0] + '.o')
+        if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
+            return obj, False
+        if emul:
+            cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-DCPU_EMUL', '-x', 'c++',
+                   '-I', HERE, '-I', os.path.join(ROOT, 'tests', 'emul'),
+                   '-Wno-unused-variable', '-c', src, '-o', obj]
+        else:
+            cmd = [NVCC] + ARCH + ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
+                                  '-I', HERE, '-c', src, '-o', obj]
+            if verbose:
+                cmd += ['-Xptxas', '-v']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('compile failed: %s\n%s' % (' '.join(cmd), r.stderr[-4000:]))
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj, True
+
+    jobs = jobs or os.cpu_count() or 4
+    with ThreadPoolExecutor(jobs) as ex:
+        res = list(ex.map(compile_one, srcs))
+    objs = [o for o, _ in res]
+    if any(c for _, c in res) or not os.path.exists(out):
+        if emul:
+            cmd = ['g++', '-shared', '-o', out] + objs
+        else:
+            cmd = [NVCC] + ARCH + ['-shared', '-o', out] + objs
+        subprocess.check_call(cmd)
+    return out
+
+
+if __name__ == '__main__':
+    print(build(emul='--emul' in sys.argv, verbose='-v' in sys.argv))

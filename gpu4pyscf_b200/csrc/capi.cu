@@ -1,0 +1,206 @@
+// C-ABI of libgvhf_rys_b200.so (declared in include/gvhf_rys_b200.h).
+#include <stdio.h>
+#include <string.h>
+#include "rt.h"
+#include "jk_launch.cuh"
+#include "qcond.cuh"
+#include "rys_tables.h"
+#include "gen/jk_dispatch.inc"
+
+#define MAX_DEVICES 64
+static double *g_cheb[MAX_DEVICES];
+static double *g_large[MAX_DEVICES];
+
+template <int LI, int LJ>
+static int qcond_launch(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,
+                        int nprim_i, int nprim_j, int dev, cudaStream_t stream)
+{
+    int nt = 64;
+    int grid = (npairs + nt - 1) / nt;
+    KLAUNCH((qcond_kernel<LI, LJ>), grid, nt, 0, stream, q_out, pairs, npairs,
+            (const int *)envs->bas, (const double *)envs->env, envs->nbas, nprim_i, nprim_j,
+            (const double *)g_cheb[dev], (const double *)g_large[dev]);
+    return rt_last_error("qcond_kernel");
+}
+
+
+// dm_cond[i,j] = log(max_{n, a in i, b in j} |D_n[a,b]| + 1e-300) per shell pair
+// (reference: condense('absmax', ...) + log, gpu4pyscf/scf/jk.py:510-514).
+__global__ void condense_kernel(float *out, const double *dm, int n_dm, int nao,
+                                const int *ao_loc, int nbas)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nbas * nbas) return;
+    int i = n / nbas, j = n - i * nbas;
+    int i0 = ao_loc[i], i1 = ao_loc[i + 1], j0 = ao_loc[j], j1 = ao_loc[j + 1];
+    double m = 0.;
+    for (int k = 0; k < n_dm; ++k) {
+        const double *d = dm + (size_t)k * nao * nao;
+        for (int a = i0; a < i1; ++a)
+            for (int b = j0; b < j1; ++b) m = fmax(m, fabs(d[(size_t)a * nao + b]));
+    }
+    out[n] = (float)log(m + 1e-300);
+}
+
+extern "C" {
+
+int RYS_b200_init(void)
+{
+    int dev = rt_device();
+    if (dev < 0 || dev >= MAX_DEVICES) return 1;
+    if (g_cheb[dev] == nullptr) {
+        g_cheb[dev] = (double *)rt_upload(RYS_CHEB_HOST, sizeof(RYS_CHEB_HOST));
+        g_large[dev] = (double *)rt_upload(RYS_LARGE_HOST, sizeof(RYS_LARGE_HOST));
+        if (g_cheb[dev] == nullptr || g_large[dev] == nullptr) {
+            fprintf(stderr, "RYS_b200_init: table upload failed\n");
+            return 1;
+        }
+    }
+    return 0;
+}
+
+int RYS_b200_lmax(void) { return LMAX_B200; }
+
+int cuda_version(void)
+{
+#ifdef CPU_EMUL
+    return 0;
+#else
+    return CUDART_VERSION;
+#endif
+}
+
+static inline int nf_of(int l) { return (l + 1) * (l + 2) / 2; }
+
+int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
+                        const RysIntEnvVars *envs, const int *lprim,
+                        const uint32_t *pair_x, const float *q_x, int npair_x,
+                        const uint32_t *pair_y, const float *q_y, int npair_y,
+                        const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
+                        int dedupe, int rank, int world, int *head, void *stream)
+{
+    if (npair_x <= 0 || npair_y <= 0) return 0;
+    if (RYS_b200_init()) return 1;
+    int dev = rt_device();
+    int lp = lprim[0], lq = lprim[1], lr = lprim[2], ls = lprim[3];
+    if (lp > LMAX_B200 || lq > LMAX_B200 || lr > LMAX_B200 || ls > LMAX_B200) {
+        fprintf(stderr, "B200_build_jk_class: l > %d is not supported\n", LMAX_B200);
+        return 1;
+    }
+    JKTask t;
+    memset(&t, 0, sizeof(t));
+    t.nao = nao;
+    t.nbas = envs->nbas;
+    t.bas = envs->bas;
+    t.env = envs->env;
+    t.ao_loc = envs->ao_loc;
+    t.pair_x = pair_x; t.pair_y = pair_y;
+    t.q_x = q_x; t.q_y = q_y;
+    t.npair_x = npair_x; t.npair_y = npair_y;
+    t.dm_cond = dm_cond;
+    t.cutoff = cutoff;
+    t.dm_penalty = dm_penalty;
+    t.q_margin = q_margin;
+    t.dedupe = dedupe;
+    t.head = head;
+    t.rank = rank;
+    t.world = world < 1 ? 1 : world;
+    t.nprim_p = lprim[4]; t.nprim_q = lprim[5]; t.nprim_r = lprim[6]; t.nprim_s = lprim[7];
+    t.rys_cheb = g_cheb[dev];
+    t.rys_large = g_large[dev];
+    int nsm = rt_num_sm();
+    int smem_max = rt_smem_max();
+    size_t nao2 = (size_t)nao * nao;
+    // the kernels digest 2 or 1 density matrices per pass
+    int i0 = 0;
+    while (i0 < n_dm) {
+        int ndm = (n_dm - i0 >= 2) ? 2 : 1;
+        jk_launcher_t fn = jk_find_launcher(lp, lq, lr, ls, ndm);
+        if (fn == nullptr) {
+            fprintf(stderr, "B200_build_jk_class: no kernel for class (%d%d|%d%d)\n", lp, lq, lr, ls);
+            return 1;
+        }
+        t.vj = vj ? vj + i0 * nao2 : nullptr;
+        t.vk = vk ? vk + i0 * nao2 : nullptr;
+        t.dm = dm + i0 * nao2;
+        t.n_dm = ndm;
+        if (i0 > 0) {
+#ifdef CPU_EMUL
+            *head = 0;
+#else
+            cudaMemsetAsync(head, 0, sizeof(int), (cudaStream_t)stream);
+#endif
+        }
+        if (fn(&t, nsm, smem_max, (cudaStream_t)stream)) return 1;
+        i0 += ndm;
+    }
+    return 0;
+}
+
+int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
+                 RysIntEnvVars *envs, int *shls_slice, int shm_size,
+                 int npairs_ij, int npairs_kl,
+                 uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
+                 float *q_cond_ij, float *q_cond_kl,
+                 float *s_cond_ij, float *s_cond_kl,
+                 float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
+                 uint32_t *pool, int *bas, double *env)
+{
+    int ish0 = shls_slice[0], jsh0 = shls_slice[2], ksh0 = shls_slice[4], lsh0 = shls_slice[6];
+    int li = bas[ish0 * BAS_SLOTS + ANG_OF], lj = bas[jsh0 * BAS_SLOTS + ANG_OF];
+    int lk = bas[ksh0 * BAS_SLOTS + ANG_OF], ll = bas[lsh0 * BAS_SLOTS + ANG_OF];
+    int ni = bas[ish0 * BAS_SLOTS + NPRIM_OF], nj = bas[jsh0 * BAS_SLOTS + NPRIM_OF];
+    int nk = bas[ksh0 * BAS_SLOTS + NPRIM_OF], nl = bas[lsh0 * BAS_SLOTS + NPRIM_OF];
+    int *head = (int *)pool;
+#ifdef CPU_EMUL
+    *head = 0;
+#else
+    cudaMemsetAsync(head, 0, sizeof(int), 0);
+#endif
+    // orientation: the pair with more Cartesian components is the register tile (X)
+    bool kl_is_x = nf_of(lk) * nf_of(ll) > nf_of(li) * nf_of(lj)
+                || (nf_of(lk) * nf_of(ll) == nf_of(li) * nf_of(lj) && lk * 8 + ll >= li * 8 + lj);
+    // the tile side must also be the side with li >= lj ordering of the instantiation list
+    if (kl_is_x) {
+        int lprim[8] = {li, lj, lk, ll, ni, nj, nk, nl};
+        return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
+                                   pair_kl_mapping, q_cond_kl, npairs_kl,
+                                   pair_ij_mapping, q_cond_ij, npairs_ij,
+                                   dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr);
+    } else {
+        int lprim[8] = {lk, ll, li, lj, nk, nl, ni, nj};
+        return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
+                                   pair_ij_mapping, q_cond_ij, npairs_ij,
+                                   pair_kl_mapping, q_cond_kl, npairs_kl,
+                                   dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr);
+    }
+}
+
+int B200_qcond(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,
+               int li, int lj, int nprim_i, int nprim_j, void *stream)
+{
+    if (npairs <= 0) return 0;
+    if (RYS_b200_init()) return 1;
+    int dev = rt_device();
+    cudaStream_t s = (cudaStream_t)stream;
+#define QC(I, J) case I * 8 + J: return qcond_launch<I, J>(q_out, envs, pairs, npairs, nprim_i, nprim_j, dev, s)
+    switch (li * 8 + lj) {
+        QC(0, 0); QC(1, 0); QC(1, 1); QC(2, 0); QC(2, 1); QC(2, 2);
+        QC(3, 0); QC(3, 1); QC(3, 2); QC(3, 3);
+        QC(4, 0); QC(4, 1); QC(4, 2); QC(4, 3); QC(4, 4);
+    }
+#undef QC
+    fprintf(stderr, "B200_qcond: unsupported pair type (%d,%d)\n", li, lj);
+    return 1;
+}
+
+int B200_condense(float *out, const double *dm, int n_dm, int nao, const int *ao_loc, int nbas,
+                  void *stream)
+{
+    int nt = 128;
+    int grid = (nbas * nbas + nt - 1) / nt;
+    KLAUNCH(condense_kernel, grid, nt, 0, (cudaStream_t)stream, out, dm, n_dm, nao, ao_loc, nbas);
+    return rt_last_error("condense_kernel");
+}
+
+}   // extern "C"

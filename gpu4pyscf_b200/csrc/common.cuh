@@ -1,0 +1,101 @@
+// Shared definitions for the sm_100a direct-SCF J/K kernels.
+//
+// Data model (libcint slot layout, mirrored by the reference at
+// gpu4pyscf/lib/gvhf-rys/vhf.cuh:5-25 and consumed through the RysIntEnvVars
+// struct, vhf.cuh:47-54 / gpu4pyscf/gto/mole.py:1054-1082).
+#pragma once
+#include <stdint.h>
+
+#ifdef CPU_EMUL
+#include "cuda_shim.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#define ATOM_OF       0
+#define ANG_OF        1
+#define NPRIM_OF      2
+#define NCTR_OF       3
+#define PTR_EXP       5
+#define PTR_COEFF     6
+#define PTR_BAS_COORD 7
+#define BAS_SLOTS     8
+
+#define LMAX_B200 4           // highest angular momentum handled on the GPU
+#define PI_FAC 34.98683665524972497   // 2*pi^2.5
+
+struct RysIntEnvVars {
+    int natm;
+    int nbas;
+    int *atm;       // device
+    int *bas;       // device
+    double *env;    // device
+    int *ao_loc;    // device
+};
+
+// One class launch: quartets (pq|rs), X = (r,s) pairs are block-resident ("tile
+// side": their Cartesian components live in one thread's registers), Y = (p,q)
+// pairs are streamed and their components are spread over threads.
+struct JKTask {
+    double *vj;             // [n_dm, nao, nao] or null
+    double *vk;             // [n_dm, nao, nao] or null
+    const double *dm;       // [n_dm, nao, nao]
+    int n_dm;
+    int nao;
+    int nbas;
+    const int *bas;         // device copies
+    const double *env;
+    const int *ao_loc;
+    const uint32_t *pair_x; // ish*nbas+jsh, sorted by q_x descending
+    const uint32_t *pair_y;
+    const float *q_x;
+    const float *q_y;
+    int npair_x;
+    int npair_y;
+    const float *dm_cond;   // [nbas, nbas] log max|D_block|
+    float cutoff;           // log(direct_scf_tol)
+    float dm_penalty;       // max(dm_cond)
+    float q_margin;         // 0 for exactly q-sorted Y lists; 4 for the reference's binned order
+    int dedupe;             // 0: none; 1: same list, keep iy >= ix (1/2 on ix==iy);
+                            // 2: keep pair_id(ij) >= pair_id(kl) (reference semantics); 3: reverse of 2
+    int x_is_bra;           // only for dedupe 2/3 bookkeeping
+    int *head;              // device work counter (zeroed by the launcher)
+    int rank;               // items item%world==rank are processed by this device
+    int world;
+    int nprim_p, nprim_q, nprim_r, nprim_s;
+    const double *rys_cheb; // device tables (rys_tables.h)
+    const double *rys_large;
+    int nq;                 // quartet slots per block
+    int slot_doubles;       // shared-memory doubles per slot
+};
+
+// ---- Cartesian component tables (lexical order xx, xy, xz, yy, yz, zz ...;
+// same convention as libcint / the reference's rys_constant.cu:21-112, but
+// computed, not tabulated).
+__host__ __device__ constexpr int ncart(int l) { return (l + 1) * (l + 2) / 2; }
+
+__host__ __device__ constexpr int cart_x(int l, int n)
+{
+    // n-th lexical component: x runs l..0, y runs l-x..0
+    int idx = 0;
+    for (int x = l; x >= 0; --x) {
+        int cnt = l - x + 1;
+        if (n < idx + cnt) return x;
+        idx += cnt;
+    }
+    return 0;
+}
+__host__ __device__ constexpr int cart_y(int l, int n)
+{
+    int idx = 0;
+    for (int x = l; x >= 0; --x) {
+        int cnt = l - x + 1;
+        if (n < idx + cnt) return (l - x) - (n - idx);
+        idx += cnt;
+    }
+    return 0;
+}
+__host__ __device__ constexpr int cart_z(int l, int n)
+{
+    return l - cart_x(l, n) - cart_y(l, n);
+}

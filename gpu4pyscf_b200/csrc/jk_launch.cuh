@@ -1,0 +1,46 @@
+// Launch-shape selection for one class instantiation (plays the role of the
+// reference's threads_scheme_for_k, gpu4pyscf/lib/gvhf-rys/rys_contract_k.cu:542-597).
+#pragma once
+#include "rt.h"
+#include "rys_jk_kernel.cuh"
+
+#define JK_TARGET_THREADS 256
+
+typedef int (*jk_launcher_t)(JKTask *t, int nsm, int smem_max, cudaStream_t stream);
+
+template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
+int jk_launch(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
+{
+    typedef JKCfg<LP, LQ, LR, LS, NCS> C;
+    static_assert(C::G <= 1024, "too many threads per quartet");
+    int npq = t->nprim_p * t->nprim_q;
+    int nrs = t->nprim_r * t->nprim_s;
+    if (npq > JK_MAXPP || nrs > JK_MAXPP) {
+        fprintf(stderr, "rys_jk: more than %d primitive pairs per shell pair\n", JK_MAXPP);
+        return 1;
+    }
+    int slot = jk_slot_doubles(npq, C::NROOTS, C::G2SIZE, C::GSIZE);
+    int nq = JK_TARGET_THREADS / C::G;
+    if (nq < 1) nq = 1;
+    while (nq > 1 && (jk_blk_doubles(NDM, C::NFRS, nq * C::G, nq) + nq * slot) * 8 > smem_max / 2) --nq;
+    int smem = (jk_blk_doubles(NDM, C::NFRS, nq * C::G, nq) + nq * slot) * 8;
+    if (smem > smem_max) {
+        fprintf(stderr, "rys_jk: class (%d%d|%d%d) needs %d B of shared memory\n", LP, LQ, LR, LS, smem);
+        return 1;
+    }
+    t->nq = nq;
+    t->slot_doubles = slot;
+    int nt = nq * C::G;
+    int per_sm = rt_prepare(rys_jk_kernel<LP, LQ, LR, LS, NCS, NDM>, smem, nt);
+    if (per_sm < 1) {
+        fprintf(stderr, "rys_jk: class (%d%d|%d%d) cannot be made resident (smem %d, threads %d)\n",
+                LP, LQ, LR, LS, smem, nt);
+        return 1;
+    }
+    int nitems = (t->npair_x + t->world - 1) / t->world;
+    int grid = nsm * per_sm;
+    if (grid > nitems) grid = nitems;
+    if (grid < 1) return 0;
+    KLAUNCH((rys_jk_kernel<LP, LQ, LR, LS, NCS, NDM>), grid, nt, smem, stream, *t);
+    return rt_last_error("rys_jk_kernel");
+}

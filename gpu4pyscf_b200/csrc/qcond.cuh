@@ -1,0 +1,103 @@
+// Schwarz bounds q_ij = 1/2 log max_ab |(ab|ab)| per shell pair, FP64 throughout.
+// Counterpart of the reference's int2e_qcond_kernel
+// (gpu4pyscf/lib/gvhf-rys/nr_sr_estimator.cu:99-396), which evaluates the same
+// quantity in FP32; here one thread owns one shell pair and only the diagonal
+// elements g(a,b,a,b) of the 2D integrals are transferred.
+#pragma once
+#include "common.cuh"
+#include "rys_roots.cuh"
+
+template <int LI, int LJ>
+__global__ void qcond_kernel(float *q_out, const uint32_t *pairs, int npairs,
+                             const int *bas, const double *env, int nbas,
+                             int nprim_i, int nprim_j,
+                             const double *cheb, const double *large)
+{
+    constexpr int L2 = LI + LJ;
+    constexpr int NROOTS = L2 + 1;
+    constexpr int NFI = ncart(LI), NFJ = ncart(LJ);
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npairs) return;
+    uint32_t pair = pairs[n];
+    int ish = pair / nbas;
+    int jsh = pair - ish * nbas;
+    const double *Ri = env + bas[ish * BAS_SLOTS + PTR_BAS_COORD];
+    const double *Rj = env + bas[jsh * BAS_SLOTS + PTR_BAS_COORD];
+    const double *ei = env + bas[ish * BAS_SLOTS + PTR_EXP];
+    const double *ej = env + bas[jsh * BAS_SLOTS + PTR_EXP];
+    const double *ci = env + bas[ish * BAS_SLOTS + PTR_COEFF];
+    const double *cj = env + bas[jsh * BAS_SLOTS + PTR_COEFF];
+    double AB[3] = {Ri[0] - Rj[0], Ri[1] - Rj[1], Ri[2] - Rj[2]};
+    double rr2 = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+    double val[NFI][NFJ];
+    for (int a = 0; a < NFI; ++a)
+        for (int b = 0; b < NFJ; ++b) val[a][b] = 0.;
+    int npp = nprim_i * nprim_j;
+    for (int ij = 0; ij < npp; ++ij) {
+        int ip = ij / nprim_j, jp = ij - ip * nprim_j;
+        double ai = ei[ip], aj = ej[jp];
+        double zeta = ai + aj;
+        double f1 = aj / zeta;
+        double P[3] = {Ri[0] - f1 * AB[0], Ri[1] - f1 * AB[1], Ri[2] - f1 * AB[2]};
+        double cij = ci[ip] * cj[jp] * exp(-ai * f1 * rr2);
+        for (int kl = 0; kl < npp; ++kl) {
+            int kp = kl / nprim_j, lp = kl - kp * nprim_j;
+            double ak = ei[kp], al = ej[lp];
+            double eta = ak + al;
+            double f2 = al / eta;
+            double Q[3] = {Ri[0] - f2 * AB[0], Ri[1] - f2 * AB[1], Ri[2] - f2 * AB[2]};
+            double ckl = ci[kp] * cj[lp] * exp(-ak * f2 * rr2);
+            double ze = zeta + eta;
+            double dx = P[0] - Q[0], dy = P[1] - Q[1], dz = P[2] - Q[2];
+            double x = zeta * eta / ze * (dx * dx + dy * dy + dz * dz);
+            double fac = PI_FAC * cij * ckl / (zeta * eta * sqrt(ze));
+            for (int root = 0; root < NROOTS; ++root) {
+                double rt_aa = rys_value<NROOTS>(root, x, cheb, large) / ze;
+                double w = rys_value<NROOTS>(NROOTS + root, x, cheb, large) * fac;
+                double rt_aij = rt_aa * eta, rt_akl = rt_aa * zeta;
+                double b00 = .5 * rt_aa;
+                double b10 = .5 / zeta * (1. - rt_aij);
+                double b01 = .5 / eta * (1. - rt_akl);
+                double diag[3][LI + 1][LJ + 1];
+                for (int axis = 0; axis < 3; ++axis) {
+                    double PQ = P[axis] - Q[axis];
+                    double c0p = (P[axis] - Ri[axis]) - rt_aij * PQ;
+                    double cpq = (Q[axis] - Ri[axis]) + rt_akl * PQ;
+                    double g[L2 + 1][L2 + 1];    // [f][e]
+                    g[0][0] = (axis == 2) ? w : 1.;
+                    for (int e = 0; e < L2; ++e)
+                        g[0][e + 1] = c0p * g[0][e] + (e > 0 ? e * b10 * g[0][e - 1] : 0.);
+                    for (int f = 0; f < L2; ++f)
+                        for (int e = 0; e <= L2; ++e)
+                            g[f + 1][e] = cpq * g[f][e] + (f > 0 ? f * b01 * g[f - 1][e] : 0.)
+                                        + (e > 0 ? e * b00 * g[f][e - 1] : 0.);
+                    for (int ea = 0; ea <= LI; ++ea) {
+                        for (int eb = 0; eb <= LJ; ++eb) {
+                            double v[L2 + 1];
+                            for (int f = 0; f <= L2; ++f) {
+                                double u[LJ + 1];
+                                for (int e = 0; e <= eb; ++e) u[e] = g[f][ea + e];
+                                for (int k = 0; k < eb; ++k)
+                                    for (int e = 0; e < eb - k; ++e) u[e] = u[e + 1] + AB[axis] * u[e];
+                                v[f] = u[0];
+                            }
+                            // ket transfer to (c = ea, d = eb)
+                            for (int d = 0; d < eb; ++d)
+                                for (int c = 0; c < L2 - d; ++c) v[c] = v[c + 1] + AB[axis] * v[c];
+                            diag[axis][ea][eb] = v[ea];
+                        }
+                    }
+                }
+                for (int a = 0; a < NFI; ++a)
+                    for (int b = 0; b < NFJ; ++b)
+                        val[a][b] += diag[0][cart_x(LI, a)][cart_x(LJ, b)]
+                                   * diag[1][cart_y(LI, a)][cart_y(LJ, b)]
+                                   * diag[2][cart_z(LI, a)][cart_z(LJ, b)];
+            }
+        }
+    }
+    double vmax = 0.;
+    for (int a = 0; a < NFI; ++a)
+        for (int b = 0; b < NFJ; ++b) vmax = fmax(vmax, fabs(val[a][b]));
+    q_out[n] = vmax > 1e-300 ? (float)(.5 * log(vmax)) : -700.f;
+}

@@ -1,0 +1,68 @@
+"""ctypes loader for libgvhf_rys_b200.so (reference: gpu4pyscf/lib/utils.py:31-36
+``load_library`` + gpu4pyscf/scf/jk.py:42-47).
+
+There is NO CPU fallback: if the CUDA library is missing the import of the J/K
+plugin fails.  The only exception is the SIMT *emulator* build of the very same
+kernel sources (tests/emul), which the CPU-only test-suite opts into with
+GPU4PYSCF_B200_EMUL=1 to debug the kernels without a GPU.
+"""
+import os
+import ctypes
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = None
+
+
+def emulated():
+    return os.environ.get('GPU4PYSCF_B200_EMUL', '0') == '1'
+
+
+def device():
+    import torch
+    if emulated():
+        return torch.device('cpu')
+    if not torch.cuda.is_available():
+        raise RuntimeError('gpu4pyscf_b200 needs a CUDA device (sm_100a); none is visible')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def load_library(name='libgvhf_rys_b200'):
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if emulated():
+        path = os.path.join(_ROOT, 'tests', 'emul', name + '_emul.so')
+    else:
+        path = os.path.join(_HERE, name + '.so')
+    if not os.path.exists(path):
+        raise ImportError(
+            f'{path} not found: build it with `python -m gpu4pyscf_b200.csrc.build` '
+            '(the J/K path has no CPU fallback)')
+    lib = ctypes.CDLL(path)
+    c_int, c_float, vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+    lib.RYS_b200_init.restype = c_int
+    lib.RYS_b200_lmax.restype = c_int
+    lib.cuda_version.restype = c_int
+    lib.B200_build_jk_class.restype = c_int
+    lib.B200_build_jk_class.argtypes = [
+        vp, vp, vp, c_int, c_int, vp, vp,
+        vp, vp, c_int, vp, vp, c_int,
+        vp, c_float, c_float, c_float, c_int, c_int, c_int, vp, vp]
+    lib.RYS_build_jk.restype = c_int
+    lib.RYS_build_jk.argtypes = [
+        vp, vp, vp, c_int, c_int, vp, vp, c_int, c_int, c_int,
+        vp, vp, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp, vp]
+    lib.B200_qcond.restype = c_int
+    lib.B200_qcond.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.B200_condense.restype = c_int
+    lib.B200_condense.argtypes = [vp, vp, c_int, c_int, vp, c_int, vp]
+    _LIB = lib
+    return lib
+
+
+def current_stream_ptr():
+    import torch
+    if emulated():
+        return None
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

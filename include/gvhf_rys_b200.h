@@ -1,0 +1,94 @@
+/*
+ * C-ABI of libgvhf_rys_b200.so -- the sm_100a direct-SCF J/K path.
+ *
+ * Drop-in boundary for the reference's libgvhf_rys entry points used by
+ * gpu4pyscf/scf/jk.py (loaded there with numpy.ctypeslib / ctypes,
+ * gpu4pyscf/scf/jk.py:42-47).  All pointers are raw DEVICE pointers unless
+ * marked HOST; no ownership is transferred; outputs are accumulated (+=) into
+ * caller-zeroed buffers; every function returns 0 on success, non-zero on
+ * failure (the Python side raises RuntimeError, jk.py:584-585).  Launches are
+ * asynchronous on the stream given (or the legacy default stream for the
+ * reference-signature entry points, as in the reference).
+ */
+#ifndef GVHF_RYS_B200_H
+#define GVHF_RYS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same field order as the reference struct (lib/gvhf-rys/vhf.cuh:47-54,
+ * gpu4pyscf/gto/mole.py:1054-1082): a HOST struct holding device pointers. */
+typedef struct {
+    int natm;
+    int nbas;
+    int *atm;
+    int *bas;
+    double *env;
+    int *ao_loc;
+} RysIntEnvVars;
+
+/* Upload the Rys root/weight tables to the current device (idempotent,
+ * per-device).  Called implicitly by the entry points below.
+ * Replaces the static __device__ tables of lib/gvhf-rys/rys_roots_dat.cu. */
+int RYS_b200_init(void);
+
+/* Highest angular momentum the GPU path evaluates (reference: LMAX = 4,
+ * lib/gvhf-rys/vhf.cuh:26, scf/jk.py:49). */
+int RYS_b200_lmax(void);
+
+/* Replaces cuda_version() of lib/gvhf-rys/rys_jk_driver.cu:51. */
+int cuda_version(void);
+
+/* Reference signature: RYS_build_jk, lib/gvhf-rys/rys_contract_jk.cu:344-454,
+ * called from gpu4pyscf/scf/jk.py:564-583.  One launch per (i,j,k,l) group of
+ * (l, nprim)-sorted shells; quartets are de-duplicated by
+ * pair_ij >= pair_kl (pair id = ish*nbas+jsh); vj/vk receive the partial
+ * (un-symmetrised) sums of jk.py:594-616.  pool must hold at least one int;
+ * bas and env are HOST copies (only bas is read, for l and nprim).
+ * s_cond_*, diffuse_exps and shm_size are accepted for signature
+ * compatibility and ignored (omega == 0 path). */
+int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
+                 RysIntEnvVars *envs, int *shls_slice, int shm_size,
+                 int npairs_ij, int npairs_kl,
+                 uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
+                 float *q_cond_ij, float *q_cond_kl,
+                 float *s_cond_ij, float *s_cond_kl,
+                 float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
+                 uint32_t *pool, int *bas, double *env);
+
+/* Native entry: one angular class (pq|rs).
+ *   lprim  HOST int[8] = {lp, lq, lr, ls, nprim_p, nprim_q, nprim_r, nprim_s}
+ *   X = (r,s) pair list (block-resident side, nf_r*nf_s >= nf_p*nf_q),
+ *   Y = (p,q) pair list (streamed); both sorted by q descending.
+ *   dedupe 0: all X x Y quartets; 1: X and Y are the same list, keep iy >= ix;
+ *          2/3: keep pair_x >= pair_y / pair_y >= pair_x (reference semantics).
+ *   q_margin: 0 for exactly sorted q_y, 4 for the reference's binned order.
+ *   rank/world: X pairs ix with ix % world == rank are processed (multi-GPU
+ *   partition of the q-sorted list); head: zeroed device int work counter.
+ * vj or vk may be NULL (K-only / J-only).  n_dm is arbitrary. */
+int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
+                        const RysIntEnvVars *envs, const int *lprim,
+                        const uint32_t *pair_x, const float *q_x, int npair_x,
+                        const uint32_t *pair_y, const float *q_y, int npair_y,
+                        const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
+                        int dedupe, int rank, int world, int *head, void *stream);
+
+/* Schwarz bounds q = 1/2 log max|(ij|ij)| for a list of shell pairs of one
+ * (li, lj, nprim_i, nprim_j) class.  Replaces int2e_qcond_estimator,
+ * lib/gvhf-rys/nr_sr_estimator.cu:416-430 (called from scf/jk.py:1076-1086). */
+int B200_qcond(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,
+               int li, int lj, int nprim_i, int nprim_j, void *stream);
+
+/* dm_cond[i*nbas+j] = log(max |D_n[a,b]| + 1e-300) over the AO block of shell
+ * pair (i,j) and all n_dm matrices.  Replaces the CuPy RawKernel behind
+ * condense('absmax', ...) (gpu4pyscf/lib/cupy_helper.py:1068-1184, used at
+ * scf/jk.py:510-514). */
+int B200_condense(float *out, const double *dm, int n_dm, int nao, const int *ao_loc, int nbas,
+                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

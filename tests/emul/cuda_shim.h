@@ -1,0 +1,71 @@
+// TEST INFRASTRUCTURE ONLY -- a minimal single-host-thread SIMT emulator.
+//
+// The build container has no GPU, so the kernel sources under
+// gpu4pyscf_b200/csrc are also compiled with g++ -DCPU_EMUL against this shim:
+// every CUDA thread of a block becomes a ucontext fiber, __syncthreads() yields
+// to the next fiber, blocks run one after another, atomics are plain adds.
+// It exists to debug index arithmetic and recurrences before spending GPU
+// minutes; it is never loaded by the product path (gpu4pyscf_b200/lib/loader.py
+// only opens it when GPU4PYSCF_B200_EMUL=1 is set by the CPU test-suite).
+#pragma once
+#include <ucontext.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <math.h>
+#include <vector>
+#include <functional>
+#include <algorithm>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __constant__ static
+#define EMUL_SHARED static
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct uint3_ { unsigned x, y, z; };
+
+extern uint3_ threadIdx, blockIdx;
+extern dim3 blockDim, gridDim;
+extern char *emul_dynamic_smem;
+
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+#define cudaSuccess 0
+
+void emul_yield();
+void emul_run_block(std::function<void()> body, unsigned nthreads);
+
+static inline void __syncthreads() { emul_yield(); }
+static inline void __syncwarp(unsigned = 0xffffffff) {}
+static inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline double __ldg(const double *p) { return *p; }
+static inline float __ldg(const float *p) { return *p; }
+static inline int __ldg(const int *p) { return *p; }
+static inline uint32_t __ldg(const uint32_t *p) { return *p; }
+static inline double rsqrt(double x) { return 1. / sqrt(x); }
+
+template <class K, class... Args>
+void emul_launch(K kernel, dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    gridDim = grid;
+    blockDim = block;
+    std::vector<char> buf(smem + 64);
+    for (unsigned b = 0; b < grid.x; ++b) {
+        blockIdx.x = b; blockIdx.y = 0; blockIdx.z = 0;
+        memset(buf.data(), 0xff, buf.size());   // poison: NaN doubles expose uninitialised reads
+        emul_dynamic_smem = buf.data();
+        emul_run_block([&]() { kernel(args...); }, block.x * block.y * block.z);
+    }
+}

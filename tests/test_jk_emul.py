@@ -1,0 +1,47 @@
+"""CPU-only checks of the CUDA kernel SOURCES through the SIMT emulator
+(tests/emul): the same .cu/.cuh files compiled with g++, every CUDA thread a
+fiber.  This is a debugging aid for a GPU-less container, not a product path."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import os, sys
+os.environ['GPU4PYSCF_B200_EMUL'] = '1'
+sys.path.insert(0, %r)
+import numpy as np
+from gpu4pyscf_b200.csrc import build
+build.build(emul=True)
+from gpu4pyscf_b200.scf import jk
+from oracle import oracle
+from tests import molecules
+case, hermi = sys.argv[1], int(sys.argv[2])
+if case == 'sto':
+    mol = molecules.water('sto-3g')
+else:
+    mol = molecules.mol1_lmax(int(case))
+np.random.seed(1)
+nao = mol.nao
+dm = np.random.rand(2, nao, nao)
+if hermi == 1:
+    dm = dm + dm.transpose(0, 2, 1)
+elif hermi == 2:
+    dm = dm - dm.transpose(0, 2, 1)
+vj, vk = jk.get_jk(mol, dm, hermi=hermi)
+rj, rk = oracle.get_jk(mol, dm, hermi=0)
+if hermi != 2:
+    assert abs(vj.numpy() - rj).max() < 1e-10, abs(vj.numpy() - rj).max()
+assert abs(vk.numpy() - rk).max() < 1e-10, abs(vk.numpy() - rk).max()
+print('OK')
+''' % ROOT
+
+
+@pytest.mark.parametrize('case,hermi', [('sto', 1), ('sto', 0), ('sto', 2), ('2', 1), ('3', 0)])
+def test_emulated_kernels_match_oracle(case, hermi):
+    r = subprocess.run([sys.executable, '-c', SCRIPT, case, str(hermi)],
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
