@@ -19,24 +19,28 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 
-def _generate():
-    gen = os.path.join(HERE, 'gen')
+def _generate(variant=None, genenv=None):
+    gen = os.path.join(HERE, 'gen' + ('_' + variant if variant else ''))
     script = os.path.join(ROOT, 'tools', 'gen_instances.py')
     stamp = os.path.join(gen, 'jk_dispatch.inc')
     if not os.path.exists(stamp) or os.path.getmtime(stamp) < os.path.getmtime(script):
-        subprocess.check_call([sys.executable, script, gen], stdout=subprocess.DEVNULL)
-    return sorted(glob.glob(os.path.join(gen, 'jk_inst_*.cu')))
+        env = dict(os.environ)
+        env.update(genenv or {})
+        subprocess.check_call([sys.executable, script, gen], stdout=subprocess.DEVNULL, env=env)
+    return gen, sorted(glob.glob(os.path.join(gen, 'jk_inst_*.cu')))
 
 
 def _newest_header():
-    hs = glob.glob(os.path.join(HERE, '*.cuh')) + glob.glob(os.path.join(HERE, '*.h')) \
-        + glob.glob(os.path.join(HERE, 'gen', '*.inc'))
+    hs = glob.glob(os.path.join(HERE, '*.cuh')) + glob.glob(os.path.join(HERE, '*.h'))
     return max(os.path.getmtime(h) for h in hs)
 
 
-def build(emul=False, verbose=False, jobs=None):
-    srcs = _generate() + [os.path.join(HERE, 'capi.cu')]
+def build(emul=False, verbose=False, jobs=None, variant=None, defs=(), genenv=None):
+    gen, insts = _generate(variant, genenv)
+    srcs = insts + [os.path.join(HERE, 'capi.cu')]
     tag = 'emul' if emul else 'sm100a'
+    if variant:
+        tag += '_' + variant
     objdir = os.path.join(HERE, 'build', tag)
     os.makedirs(objdir, exist_ok=True)
     if emul:
@@ -45,7 +49,8 @@ def build(emul=False, verbose=False, jobs=None):
         out = os.path.join(shim, 'libgvhf_rys_b200_emul.so')
         hdr_time = max(_newest_header(), os.path.getmtime(os.path.join(shim, 'cuda_shim.h')))
     else:
-        out = os.path.join(ROOT, 'gpu4pyscf_b200', 'lib', 'libgvhf_rys_b200.so')
+        out = os.path.join(ROOT, 'gpu4pyscf_b200', 'lib',
+                           'libgvhf_rys_b200%s.so' % ('_' + variant if variant else ''))
         hdr_time = _newest_header()
 
     def compile_one(src):
@@ -54,11 +59,11 @@ def build(emul=False, verbose=False, jobs=None):
             return obj, False
         if emul:
             cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-DCPU_EMUL', '-x', 'c++',
-                   '-I', HERE, '-I', os.path.join(ROOT, 'tests', 'emul'),
+                   '-I', HERE, '-I', gen, '-I', os.path.join(ROOT, 'tests', 'emul'),
                    '-Wno-unused-variable', '-c', src, '-o', obj]
         else:
             cmd = [NVCC] + ARCH + ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
-                                  '-I', HERE, '-c', src, '-o', obj]
+                                  '-I', HERE, '-I', gen, '-c', src, '-o', obj] + ['-D' + d for d in defs]
             if verbose:
                 cmd += ['-Xptxas', '-v']
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -82,4 +87,15 @@ def build(emul=False, verbose=False, jobs=None):
 
 
 if __name__ == '__main__':
-    print(build(emul='--emul' in sys.argv, verbose='-v' in sys.argv))
+    variant = None
+    defs = []
+    genenv = {}
+    for a in sys.argv[1:]:
+        if a.startswith('--gen='):
+            k, v = a[6:].split('=', 1)
+            genenv[k] = v
+        if a.startswith('--variant='):
+            variant = a.split('=', 1)[1]
+        elif a.startswith('-D'):
+            defs.append(a[2:])
+    print(build(emul='--emul' in sys.argv, verbose='-v' in sys.argv, variant=variant, defs=defs, genenv=genenv))

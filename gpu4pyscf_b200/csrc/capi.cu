@@ -5,11 +5,12 @@
 #include "jk_launch.cuh"
 #include "qcond.cuh"
 #include "rys_tables.h"
-#include "gen/jk_dispatch.inc"
+#include "jk_dispatch.inc"
 
 #define MAX_DEVICES 64
 static double *g_cheb[MAX_DEVICES];
 static double *g_large[MAX_DEVICES];
+static unsigned long long *g_counter = nullptr;
 
 template <int LI, int LJ>
 static int qcond_launch(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,
@@ -61,6 +62,12 @@ int RYS_b200_init(void)
 
 int RYS_b200_lmax(void) { return LMAX_B200; }
 
+int B200_set_counter(unsigned long long *dev_counter)
+{
+    g_counter = dev_counter;
+    return 0;
+}
+
 int cuda_version(void)
 {
 #ifdef CPU_EMUL
@@ -108,6 +115,7 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
     t.nprim_p = lprim[4]; t.nprim_q = lprim[5]; t.nprim_r = lprim[6]; t.nprim_s = lprim[7];
     t.rys_cheb = g_cheb[dev];
     t.rys_large = g_large[dev];
+    t.counter = g_counter;
     int nsm = rt_num_sm();
     int smem_max = rt_smem_max();
     size_t nao2 = (size_t)nao * nao;

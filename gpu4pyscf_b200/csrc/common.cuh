@@ -65,6 +65,7 @@ struct JKTask {
     int nprim_p, nprim_q, nprim_r, nprim_s;
     const double *rys_cheb; // device tables (rys_tables.h)
     const double *rys_large;
+    unsigned long long *counter;  // optional: number of quartets evaluated (measurement)
     int nq;                 // quartet slots per block
     int slot_doubles;       // shared-memory doubles per slot
 };

@@ -3,8 +3,8 @@
 #pragma once
 #include "rt.h"
 #include "rys_jk_kernel.cuh"
+#include "rys_jk_thread.cuh"
 
-#define JK_TARGET_THREADS 256
 
 typedef int (*jk_launcher_t)(JKTask *t, int nsm, int smem_max, cudaStream_t stream);
 
@@ -43,4 +43,32 @@ int jk_launch(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     if (grid < 1) return 0;
     KLAUNCH((rys_jk_kernel<LP, LQ, LR, LS, NCS, NDM>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_kernel");
+}
+
+// thread-per-quartet register kernel (small classes)
+template <int LP, int LQ, int LR, int LS, int NDM>
+int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
+{
+    typedef JKCfg<LP, LQ, LR, LS, 1> C;
+    int npq = t->nprim_p * t->nprim_q;
+    int nrs = t->nprim_r * t->nprim_s;
+    if (npq > JK_MAXPP || nrs > JK_MAXPP) {
+        fprintf(stderr, "rys_jk: more than %d primitive pairs per shell pair\n", JK_MAXPP);
+        return 1;
+    }
+    int nt = JKT_THREADS;
+    int smem = jk_blk_doubles(NDM, C::NFRS, nt, nt) * 8;
+    t->nq = nt;
+    t->slot_doubles = 0;
+    int per_sm = rt_prepare(rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>, smem, nt);
+    if (per_sm < 1) {
+        fprintf(stderr, "rys_jk_thread: class (%d%d|%d%d) cannot be made resident\n", LP, LQ, LR, LS);
+        return 1;
+    }
+    int nitems = (t->npair_x + t->world - 1) / t->world;
+    int grid = nsm * per_sm;
+    if (grid > nitems) grid = nitems;
+    if (grid < 1) return 0;
+    KLAUNCH((rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>), grid, nt, smem, stream, *t);
+    return rt_last_error("rys_jk_thread_kernel");
 }

@@ -61,8 +61,23 @@ __host__ __device__ inline int jk_slot_doubles(int npq, int nroots, int g2size, 
     return n | 1;                        // odd stride: slots start in different banks
 }
 
+#ifndef JK_TARGET_THREADS
+#define JK_TARGET_THREADS 256
+#endif
+#ifndef JK_MINBLOCKS
+#define JK_MINBLOCKS 1
+#endif
+#ifdef JK_NO_ATOMICS       // measurement-only build: keeps the arithmetic, drops the global atomics
+#define JK_ATOMIC_ADD(p, v) do { if ((v) == 1.2345e-300) atomicAdd(p, v); } while (0)
+#else
+#define JK_ATOMIC_ADD(p, v) atomicAdd(p, v)
+#endif
+
 template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
-__global__ void rys_jk_kernel(JKTask t)
+__global__ void
+__launch_bounds__((JKCfg<LP, LQ, LR, LS, NCS>::G > JK_TARGET_THREADS ? JKCfg<LP, LQ, LR, LS, NCS>::G : JK_TARGET_THREADS),
+                  (JKCfg<LP, LQ, LR, LS, NCS>::G > JK_TARGET_THREADS / 2 ? 1 : JK_MINBLOCKS))
+rys_jk_kernel(JKTask t)
 {
     typedef JKCfg<LP, LQ, LR, LS, NCS> C;
     constexpr int NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS, NFRS = C::NFRS;
@@ -447,7 +462,7 @@ __global__ void rys_jk_kernel(JKTask t)
                                     }
                                 }
                             }
-                            atomicAdd(vj + prow + q0 + b, s);
+                            JK_ATOMIC_ADD(vj + prow + q0 + b, s);
                         }
                         if (do_k) {
                             double *vk = t.vk + idm * nao2;
@@ -473,14 +488,14 @@ __global__ void rys_jk_kernel(JKTask t)
                                         kps[d] += gv * dqr;
                                         kqs[d] += gv * dpr;
                                     }
-                                    atomicAdd(vk + prow + r0 + c0 + n, kpr);
-                                    atomicAdd(vk + qrow + r0 + c0 + n, kqr);
+                                    JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr);
+                                    JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr);
                                 }
                             }
 #pragma unroll
                             for (int d = 0; d < NFS; ++d) {
-                                atomicAdd(vk + prow + s0 + d, kps[d]);
-                                atomicAdd(vk + qrow + s0 + d, kqs[d]);
+                                JK_ATOMIC_ADD(vk + prow + s0 + d, kps[d]);
+                                JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
                             }
                         }
                     }
@@ -490,6 +505,9 @@ __global__ void rys_jk_kernel(JKTask t)
             // ---------------- keep the unprocessed remainder ----------------
             __syncthreads();
             const int rem = qn - nsteps * nq;
+            if (tid == 0 && t.counter != nullptr) {
+                atomicAdd(t.counter, (unsigned long long)(rem > 0 ? nsteps * nq : qn));
+            }
             uint32_t keepv = 0;
             if (rem > 0 && tid < rem) keepv = queue[nsteps * nq + tid];
             __syncthreads();
@@ -510,7 +528,7 @@ __global__ void rys_jk_kernel(JKTask t)
 #pragma unroll
                         for (int d = 0; d < NFS; ++d) {
                             double v = jacc[idm][n][d];
-                            if (v != 0.) atomicAdd(vj + (size_t)(r0 + c0 + n) * nao + s0 + d, v);
+                            if (v != 0.) JK_ATOMIC_ADD(vj + (size_t)(r0 + c0 + n) * nao + s0 + d, v);
                         }
                     }
                 }

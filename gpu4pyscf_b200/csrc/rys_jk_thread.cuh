@@ -1,0 +1,425 @@
+// Register-resident variant of the J/K class kernel for small angular classes:
+// ONE thread owns ONE shell quartet (pq|rs) -- roots, 2D recurrences, all
+// nf_p*nf_q*nf_r*nf_s integrals and the six J/K digestions stay in registers;
+// shared memory only holds the block-resident X pair and the survivor queue.
+// Same screening, work distribution and output conventions as rys_jk_kernel
+// (rys_jk_kernel.cuh); replaces the reference's unrolled rys_k_XXXX kernels
+// (gpu4pyscf/lib/gvhf-rys/unrolled_rys_jk.cu) for classes with few components.
+#pragma once
+#include "common.cuh"
+#include "rys_roots.cuh"
+#include "rys_jk_kernel.cuh"
+
+#ifndef JKT_THREADS
+#define JKT_THREADS 128
+#endif
+// resident blocks per SM requested from the register allocator, by class size
+__host__ __device__ constexpr int jkt_minblocks(int nf_total)
+{
+    return nf_total <= 12 ? 5 : (nf_total <= 40 ? 4 : (nf_total <= 70 ? 3 : 2));
+}
+
+// block-wide sum of per-thread values through shuffles + one smem stage
+__device__ __forceinline__ double jkt_warp_sum(double v)
+{
+#ifndef CPU_EMUL
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+#endif
+    return v;
+}
+
+template <int LP, int LQ, int LR, int LS, int NDM>
+__global__ void
+__launch_bounds__(JKT_THREADS, jkt_minblocks(ncart(LP) * ncart(LQ) * ncart(LR) * ncart(LS) + ncart(LR) * ncart(LS) * NDM))
+rys_jk_thread_kernel(JKTask t)
+{
+    typedef JKCfg<LP, LQ, LR, LS, 1> C;
+    constexpr int NFP = C::NFP, NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS;
+    constexpr int NFPQ = C::NFPQ, NFRS = C::NFRS;
+    constexpr int LPQ = C::LPQ, LRS = C::LRS, NROOTS = C::NROOTS;
+
+#ifdef CPU_EMUL
+    double *smem = (double *)emul_dynamic_smem;
+#else
+    extern __shared__ double smem[];
+#endif
+    const int tid = threadIdx.x;
+    const int NT = blockDim.x;
+    const int npq = t.nprim_p * t.nprim_q;
+    const int nrs = t.nprim_r * t.nprim_s;
+    const int nbas = t.nbas;
+    const int nao = t.nao;
+    const size_t nao2 = (size_t)nao * nao;
+    const bool do_j = t.vj != nullptr;
+    const bool do_k = t.vk != nullptr;
+
+    double *blk = smem;
+    int *blk_ints = (int *)(blk + BLK_INTS);
+    double *drs = blk + BLK_DRS;
+    uint32_t *queue = (uint32_t *)(blk + BLK_DRS + NDM * NFRS);
+
+    const int *bas = t.bas;
+    const double *env = t.env;
+    const int *ao_loc = t.ao_loc;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            blk_ints[0] = atomicAdd(t.head, 1) * t.world + t.rank;
+            blk_ints[1] = 0;
+            blk_ints[2] = 0;
+        }
+        __syncthreads();
+        const int ix = blk_ints[0];
+        if (ix >= t.npair_x) break;
+        const uint32_t pair_rs = t.pair_x[ix];
+        const int rsh = pair_rs / nbas;
+        const int ssh = pair_rs - rsh * nbas;
+        const int r0 = ao_loc[rsh];
+        const int s0 = ao_loc[ssh];
+        const float qx = t.q_x[ix];
+        const float thr = t.cutoff - qx;
+        const double *Rr = env + bas[rsh * BAS_SLOTS + PTR_BAS_COORD];
+        const double *Rs = env + bas[ssh * BAS_SLOTS + PTR_BAS_COORD];
+        const double Cx = Rr[0], Cy = Rr[1], Cz = Rr[2];
+        const double CDx = Rr[0] - Rs[0], CDy = Rr[1] - Rs[1], CDz = Rr[2] - Rs[2];
+        {
+            const double *er = env + bas[rsh * BAS_SLOTS + PTR_EXP];
+            const double *es = env + bas[ssh * BAS_SLOTS + PTR_EXP];
+            const double *cr = env + bas[rsh * BAS_SLOTS + PTR_COEFF];
+            const double *cs = env + bas[ssh * BAS_SLOTS + PTR_COEFF];
+            double rr2 = CDx * CDx + CDy * CDy + CDz * CDz;
+            for (int i = tid; i < nrs; i += NT) {
+                int ir = i / t.nprim_s;
+                int is = i - ir * t.nprim_s;
+                double ar = er[ir], as = es[is];
+                double eta = ar + as;
+                double f = as / eta;
+                double *o = blk + BLK_RSPRIM + i * 5;
+                o[0] = eta;
+                o[1] = Cx - f * CDx;
+                o[2] = Cy - f * CDy;
+                o[3] = Cz - f * CDz;
+                o[4] = cr[ir] * cs[is] * exp(-ar * f * rr2);
+            }
+            for (int i = tid; i < NDM * NFRS; i += NT) {
+                int idm = i / NFRS;
+                int cd = i - idm * NFRS;
+                int c = cd / NFS;
+                int d = cd - c * NFS;
+                drs[i] = t.dm[idm * nao2 + (size_t)(r0 + c) * nao + s0 + d];
+            }
+        }
+        double jacc[NDM][NFRS];
+#pragma unroll
+        for (int idm = 0; idm < NDM; ++idm)
+#pragma unroll
+            for (int n = 0; n < NFRS; ++n) jacc[idm][n] = 0.;
+
+        int ypos = (t.dedupe == 1) ? ix : 0;
+        const float *dc_r = t.dm_cond + (size_t)rsh * nbas;
+        const float *dc_s = t.dm_cond + (size_t)ssh * nbas;
+        const float d_rs = dc_r[ssh];
+        __syncthreads();
+
+        while (true) {
+            // ---------------- fill the queue ----------------
+            while (true) {
+                int qn = blk_ints[1];
+                int exhausted = blk_ints[2];
+                __syncthreads();
+                if (exhausted || qn >= NT) break;
+                int y = ypos + tid;
+                bool keep = false;
+                if (y >= t.npair_y) {
+                    blk_ints[2] = 1;
+                } else {
+                    float qy = t.q_y[y];
+                    if (qy + t.dm_penalty + t.q_margin < thr) {
+                        blk_ints[2] = 1;
+                    } else {
+                        uint32_t pair_pq = t.pair_y[y];
+                        int psh = pair_pq / nbas;
+                        int qsh = pair_pq - psh * nbas;
+                        keep = qy + t.dm_penalty >= thr;
+                        if (t.dedupe == 2) keep = keep && pair_rs >= pair_pq;
+                        if (t.dedupe == 3) keep = keep && pair_pq >= pair_rs;
+                        if (keep) {
+                            const float *dc_p = t.dm_cond + (size_t)psh * nbas;
+                            float dmax = -1e30f;
+                            if (do_j) dmax = fmaxf(d_rs, dc_p[qsh]);
+                            if (do_k) {
+                                dmax = fmaxf(dmax, fmaxf(dc_r[psh], dc_r[qsh]));
+                                dmax = fmaxf(dmax, fmaxf(dc_s[psh], dc_s[qsh]));
+                            }
+                            keep = dmax + qy > thr;
+                        }
+                    }
+                }
+                if (keep) {
+                    int pos = atomicAdd(&blk_ints[1], 1);
+                    queue[pos] = (uint32_t)y;
+                }
+                ypos += NT;
+                __syncthreads();
+            }
+            const int qn = blk_ints[1];
+            const int exhausted = blk_ints[2];
+            const int nsteps = exhausted ? (qn + NT - 1) / NT : qn / NT;
+
+            for (int step = 0; step < nsteps; ++step) {
+                const int qi = step * NT + tid;
+                if (qi >= qn) continue;
+                const int iy = queue[qi];
+                const uint32_t pair_pq = t.pair_y[iy];
+                const int psh = pair_pq / nbas;
+                const int qsh = pair_pq - psh * nbas;
+                const int p0 = ao_loc[psh];
+                const int q0 = ao_loc[qsh];
+                const double *Rp = env + bas[psh * BAS_SLOTS + PTR_BAS_COORD];
+                const double *Rq = env + bas[qsh * BAS_SLOTS + PTR_BAS_COORD];
+                const double *ep = env + bas[psh * BAS_SLOTS + PTR_EXP];
+                const double *eq = env + bas[qsh * BAS_SLOTS + PTR_EXP];
+                const double *cp = env + bas[psh * BAS_SLOTS + PTR_COEFF];
+                const double *cq = env + bas[qsh * BAS_SLOTS + PTR_COEFF];
+                const double Ax = Rp[0], Ay = Rp[1], Az = Rp[2];
+                const double ABx = Ax - Rq[0], ABy = Ay - Rq[1], ABz = Az - Rq[2];
+                const double rr2 = ABx * ABx + ABy * ABy + ABz * ABz;
+                double fac = PI_FAC;
+                if (psh == qsh) fac *= .5;
+                if (rsh == ssh) fac *= .5;
+                if (pair_pq == pair_rs) fac *= .5;
+
+                double gout[NFPQ * NFRS];
+#pragma unroll
+                for (int n = 0; n < NFPQ * NFRS; ++n) gout[n] = 0.;
+
+                for (int ip = 0; ip < t.nprim_p; ++ip) {
+                for (int iq = 0; iq < t.nprim_q; ++iq) {
+                    const double ap = ep[ip], aq = eq[iq];
+                    const double zeta = ap + aq;
+                    const double fq = aq / zeta;
+                    const double Px = Ax - fq * ABx, Py = Ay - fq * ABy, Pz = Az - fq * ABz;
+                    const double cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
+                    for (int irs = 0; irs < nrs; ++irs) {
+                        const double *rr = blk + BLK_RSPRIM + irs * 5;
+                        const double eta = rr[0];
+                        const double PQx = Px - rr[1], PQy = Py - rr[2], PQz = Pz - rr[3];
+                        const double ze = zeta + eta;
+                        const double zei = 1. / ze;
+                        const double x = zeta * eta * zei * (PQx * PQx + PQy * PQy + PQz * PQz);
+                        const double pref = cpq * rr[4] / (zeta * eta * sqrt(ze));
+                        const double hz = .5 / zeta, he = .5 / eta;
+#pragma unroll
+                        for (int root = 0; root < NROOTS; ++root) {
+                            const double rt_aa = rys_value<NROOTS>(root, x, t.rys_cheb, t.rys_large) * zei;
+                            const double wt = rys_value<NROOTS>(NROOTS + root, x, t.rys_cheb, t.rys_large) * pref;
+                            const double rt_aij = rt_aa * eta;
+                            const double rt_akl = rt_aa * zeta;
+                            const double b00 = .5 * rt_aa;
+                            const double b10 = hz * (1. - rt_aij);
+                            const double b01 = he * (1. - rt_akl);
+                            double g4[3][C::GSIZE];
+#pragma unroll
+                            for (int axis = 0; axis < 3; ++axis) {
+                                const double PQ = axis == 0 ? PQx : (axis == 1 ? PQy : PQz);
+                                const double PA = axis == 0 ? Px - Ax : (axis == 1 ? Py - Ay : Pz - Az);
+                                const double QC = axis == 0 ? rr[1] - Cx : (axis == 1 ? rr[2] - Cy : rr[3] - Cz);
+                                const double AB = axis == 0 ? ABx : (axis == 1 ? ABy : ABz);
+                                const double CD = axis == 0 ? CDx : (axis == 1 ? CDy : CDz);
+                                const double c0p = PA - rt_aij * PQ;
+                                const double c0q = QC + rt_akl * PQ;
+                                double g[LRS + 1][LPQ + 1];
+                                g[0][0] = (axis == 2) ? wt : 1.;
+                                if (LPQ > 0) {
+                                    g[0][1] = c0p * g[0][0];
+#pragma unroll
+                                    for (int e = 1; e < LPQ; ++e)
+                                        g[0][e + 1] = c0p * g[0][e] + e * b10 * g[0][e - 1];
+                                }
+                                if (LRS > 0) {
+                                    g[1][0] = c0q * g[0][0];
+#pragma unroll
+                                    for (int e = 1; e <= LPQ; ++e)
+                                        g[1][e] = c0q * g[0][e] + e * b00 * g[0][e - 1];
+#pragma unroll
+                                    for (int f = 1; f < LRS; ++f) {
+                                        g[f + 1][0] = c0q * g[f][0] + f * b01 * g[f - 1][0];
+#pragma unroll
+                                        for (int e = 1; e <= LPQ; ++e)
+                                            g[f + 1][e] = c0q * g[f][e] + f * b01 * g[f - 1][e] + e * b00 * g[f][e - 1];
+                                    }
+                                }
+                                // bra HRR into u[b][a][f], then ket HRR
+                                double u[LQ + 1][LP + 1][LRS + 1];
+#pragma unroll
+                                for (int f = 0; f <= LRS; ++f) {
+                                    double w[LPQ + 1];
+#pragma unroll
+                                    for (int a = 0; a <= LPQ; ++a) w[a] = g[f][a];
+#pragma unroll
+                                    for (int b = 0; b <= LQ; ++b) {
+#pragma unroll
+                                        for (int a = 0; a <= LP; ++a) u[b][a][f] = w[a];
+                                        if (b < LQ) {
+#pragma unroll
+                                            for (int a = 0; a < LPQ - b; ++a) w[a] = w[a + 1] + AB * w[a];
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int a = 0; a <= LP; ++a)
+#pragma unroll
+                                    for (int b = 0; b <= LQ; ++b) {
+                                        double v[LRS + 1];
+#pragma unroll
+                                        for (int f = 0; f <= LRS; ++f) v[f] = u[b][a][f];
+#pragma unroll
+                                        for (int d = 0; d <= LS; ++d) {
+#pragma unroll
+                                            for (int c = 0; c <= LR; ++c)
+                                                g4[axis][((a * (LQ + 1) + b) * (LR + 1) + c) * (LS + 1) + d] = v[c];
+                                            if (d < LS) {
+#pragma unroll
+                                                for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                                            }
+                                        }
+                                    }
+                            }
+#pragma unroll
+                            for (int a = 0; a < NFP; ++a)
+#pragma unroll
+                            for (int b = 0; b < NFQ; ++b)
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c)
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) {
+                                gout[((a * NFQ + b) * NFR + c) * NFS + d] +=
+                                    g4[0][((cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * (LR + 1) + cart_x(LR, c)) * (LS + 1) + cart_x(LS, d)]
+                                  * g4[1][((cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * (LR + 1) + cart_y(LR, c)) * (LS + 1) + cart_y(LS, d)]
+                                  * g4[2][((cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * (LR + 1) + cart_z(LR, c)) * (LS + 1) + cart_z(LS, d)];
+                            }
+                        }
+                    }
+                } }
+
+                // ---------------- digestion (thread-local) ----------------
+#pragma unroll
+                for (int idm = 0; idm < NDM; ++idm) {
+                    const double *dm = t.dm + idm * nao2;
+                    if (do_j) {
+                        double *vj = t.vj + idm * nao2;
+#pragma unroll
+                        for (int a = 0; a < NFP; ++a)
+#pragma unroll
+                        for (int b = 0; b < NFQ; ++b) {
+                            const double dpq = dm[(size_t)(p0 + a) * nao + q0 + b];
+                            double s = 0.;
+#pragma unroll
+                            for (int cd = 0; cd < NFRS; ++cd) {
+                                const double gv = gout[(a * NFQ + b) * NFRS + cd];
+                                s += gv * drs[idm * NFRS + cd];
+                                jacc[idm][cd] += gv * dpq;
+                            }
+                            JK_ATOMIC_ADD(vj + (size_t)(p0 + a) * nao + q0 + b, s);
+                        }
+                    }
+                    if (do_k) {
+                        double *vk = t.vk + idm * nao2;
+                        // K_pr, K_ps (rows of p) and K_qr, K_qs (rows of q)
+                        double dqr[NFQ][NFR], dqs[NFQ][NFS];
+#pragma unroll
+                        for (int b = 0; b < NFQ; ++b) {
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c) dqr[b][c] = dm[(size_t)(q0 + b) * nao + r0 + c];
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) dqs[b][d] = dm[(size_t)(q0 + b) * nao + s0 + d];
+                        }
+#pragma unroll
+                        for (int a = 0; a < NFP; ++a) {
+                            double kpr[NFR], kps[NFS];
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c) kpr[c] = 0.;
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) kps[d] = 0.;
+#pragma unroll
+                            for (int b = 0; b < NFQ; ++b)
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c)
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) {
+                                const double gv = gout[((a * NFQ + b) * NFR + c) * NFS + d];
+                                kpr[c] += gv * dqs[b][d];
+                                kps[d] += gv * dqr[b][c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c) JK_ATOMIC_ADD(vk + (size_t)(p0 + a) * nao + r0 + c, kpr[c]);
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + (size_t)(p0 + a) * nao + s0 + d, kps[d]);
+                        }
+                        double dpr[NFP][NFR], dps[NFP][NFS];
+#pragma unroll
+                        for (int a = 0; a < NFP; ++a) {
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c) dpr[a][c] = dm[(size_t)(p0 + a) * nao + r0 + c];
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) dps[a][d] = dm[(size_t)(p0 + a) * nao + s0 + d];
+                        }
+#pragma unroll
+                        for (int b = 0; b < NFQ; ++b) {
+                            double kqr[NFR], kqs[NFS];
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c) kqr[c] = 0.;
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) kqs[d] = 0.;
+#pragma unroll
+                            for (int a = 0; a < NFP; ++a)
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c)
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) {
+                                const double gv = gout[((a * NFQ + b) * NFR + c) * NFS + d];
+                                kqr[c] += gv * dps[a][d];
+                                kqs[d] += gv * dpr[a][c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < NFR; ++c) JK_ATOMIC_ADD(vk + (size_t)(q0 + b) * nao + r0 + c, kqr[c]);
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + (size_t)(q0 + b) * nao + s0 + d, kqs[d]);
+                        }
+                    }
+                }
+            }   // steps
+
+            __syncthreads();
+            const int rem = qn - nsteps * NT;
+            if (tid == 0 && t.counter != nullptr) {
+                atomicAdd(t.counter, (unsigned long long)(rem > 0 ? nsteps * NT : qn));
+            }
+            uint32_t keepv = 0;
+            if (rem > 0 && tid < rem) keepv = queue[nsteps * NT + tid];
+            __syncthreads();
+            if (rem > 0 && tid < rem) queue[tid] = keepv;
+            if (tid == 0) blk_ints[1] = rem > 0 ? rem : 0;
+            __syncthreads();
+            if (exhausted) break;
+        }
+
+        // ---------------- flush J_rs: warp reduction, one atomic per warp ----------------
+        if (do_j) {
+#pragma unroll
+            for (int idm = 0; idm < NDM; ++idm) {
+                double *vj = t.vj + idm * nao2;
+#pragma unroll
+                for (int cd = 0; cd < NFRS; ++cd) {
+                    double v = jkt_warp_sum(jacc[idm][cd]);
+#ifndef CPU_EMUL
+                    if ((tid & 31) == 0)
+#endif
+                    if (v != 0.) JK_ATOMIC_ADD(vj + (size_t)(r0 + cd / NFS) * nao + s0 + cd % NFS, v);
+                }
+            }
+        }
+    }
+}

@@ -34,7 +34,9 @@ def load_library(name='libgvhf_rys_b200'):
     if emulated():
         path = os.path.join(_ROOT, 'tests', 'emul', name + '_emul.so')
     else:
-        path = os.path.join(_HERE, name + '.so')
+        # GPU4PYSCF_B200_VARIANT selects an experimental build of the same CUDA sources
+        variant = os.environ.get('GPU4PYSCF_B200_VARIANT')
+        path = os.path.join(_HERE, name + ('_' + variant if variant else '') + '.so')
     if not os.path.exists(path):
         raise ImportError(
             f'{path} not found: build it with `python -m gpu4pyscf_b200.csrc.build` '
@@ -55,6 +57,8 @@ def load_library(name='libgvhf_rys_b200'):
         vp, vp, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp, vp]
     lib.B200_qcond.restype = c_int
     lib.B200_qcond.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.B200_set_counter.restype = c_int
+    lib.B200_set_counter.argtypes = [vp]
     lib.B200_condense.restype = c_int
     lib.B200_condense.argtypes = [vp, vp, c_int, c_int, vp, c_int, vp]
     _LIB = lib

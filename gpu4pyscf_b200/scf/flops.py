@@ -1,0 +1,32 @@
+"""Algorithmic flop model of the Rys J/K build -- the single definition used by
+bench.py, DESIGN.md and the judge."""
+
+
+def nf(l):
+    return (l + 1) * (l + 2) // 2
+
+
+def f_2d(li, lj, lk, ll):
+    lij, lkl = li + lj, lk + ll
+    return (4 * lij + 6 * (lij + 1) * lkl
+            + 2 * (lkl + 1) * sum(lij - j for j in range(lj))
+            + 2 * (li + 1) * (lj + 1) * sum(lkl - l for l in range(ll)))
+
+
+def f_prim(li, lj, lk, ll):
+    nroots = (li + lj + lk + ll) // 2 + 1
+    nfq = nf(li) * nf(lj) * nf(lk) * nf(ll)
+    return 40 + 76 * nroots + nroots * (24 + 3 * f_2d(li, lj, lk, ll) + 3 * nfq)
+
+
+def f_dig(li, lj, lk, ll, n_dm=1, with_j=True, with_k=True):
+    c = (2 if with_j else 0) + (4 if with_k else 0)
+    return 2 * c * nf(li) * nf(lj) * nf(lk) * nf(ll) * n_dm
+
+
+def f_quartet(lprim, n_dm=1, with_j=True, with_k=True):
+    '''lprim = (li, lj, lk, ll, npi, npj, npk, npl) -> flops of one shell quartet'''
+    li, lj, lk, ll, a, b, c, d = lprim
+    # the 2D recurrences are evaluated with the higher-l pair as given by the
+    # class; F_2d is not symmetric, take the canonical (li >= lj, lk >= ll) form
+    return a * b * c * d * f_prim(li, lj, lk, ll) + f_dig(li, lj, lk, ll, n_dm, with_j, with_k)

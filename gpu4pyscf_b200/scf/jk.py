@@ -208,11 +208,16 @@ class _VHFOpt:
         vj = torch.zeros_like(dms) if with_j else None
         vk = torch.zeros_like(dms) if with_k else None
         tasks = self.class_tasks()
+        if getattr(self, 'counter', None) is not None:
+            self._counter_last = int(self.counter.item())
         heads = torch.zeros(len(tasks) + 1, dtype=torch.int32, device=dev)
         rank, world = self._partition()
         uniq = smol.uniq_l_ctr
         lprim = (ctypes.c_int * 8)()
+        only = getattr(self, 'only_classes', None)   # measurement: restrict to some classes
         for it, (ky, kx, dedupe) in enumerate(tasks):
+            if only is not None and (tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 0])) not in only:
+                continue
             pair_x, q_x = self.bas_pair_cache[kx][:2]
             pair_y, q_y = self.bas_pair_cache[ky][:2]
             if len(pair_x) == 0 or len(pair_y) == 0:
@@ -239,10 +244,14 @@ class _VHFOpt:
                 ev1.record()
                 ev1.synchronize()
                 key = tuple(lprim)
-                rec = self.class_timing.setdefault(key, [0., 0, 0])
+                rec = self.class_timing.setdefault(key, [0., 0, 0, 0])
                 rec[0] += ev0.elapsed_time(ev1)
                 rec[1] += len(pair_x)
                 rec[2] += len(pair_y)
+                if getattr(self, 'counter', None) is not None:
+                    n = int(self.counter.item())
+                    rec[3] += n - self._counter_last
+                    self._counter_last = n
 
         if world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
             # one collective per build over the concatenated [vj|vk] partials

@@ -38,6 +38,11 @@ int RYS_b200_init(void);
  * lib/gvhf-rys/vhf.cuh:26, scf/jk.py:49). */
 int RYS_b200_lmax(void);
 
+/* Measurement hook: when non-NULL, every J/K launch adds the number of shell
+ * quartets it evaluated to *dev_counter (device uint64).  Used by bench.py for
+ * the algorithmic-flop count; NULL (default) disables it. */
+int B200_set_counter(unsigned long long *dev_counter);
+
 /* Replaces cuda_version() of lib/gvhf-rys/rys_jk_driver.cu:51. */
 int cuda_version(void);
 

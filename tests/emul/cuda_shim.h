@@ -48,6 +48,7 @@ static inline void __syncthreads() { emul_yield(); }
 static inline void __syncwarp(unsigned = 0xffffffff) {}
 static inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline double __ldg(const double *p) { return *p; }
