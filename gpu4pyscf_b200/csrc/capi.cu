@@ -212,3 +212,24 @@ int B200_condense(float *out, const double *dm, int n_dm, int nao, const int *ao
 }
 
 }   // extern "C"
+
+// ---- measurement: FP64 FMA peak micro-benchmark (the roofline
+// denominator is a DFMA burn measured on the same box in the same run).
+// Every thread runs `iters` rounds of 8 independent FMA chains.
+__global__ void dfma_burn_kernel(double *sink, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3.;
+    double x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+    for (int i = 0; i < iters; ++i) {
+        x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+        x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 1.2345e-300) sink[0] = s;
+}
+
+extern "C" int B200_dfma_burn(double *sink, int iters, int blocks, int threads, void *stream)
+{
+    KLAUNCH(dfma_burn_kernel, blocks, threads, 0, (cudaStream_t)stream, sink, iters, 0.999999, 1e-7);
+    return rt_last_error("dfma_burn_kernel");
+}

@@ -61,6 +61,8 @@ def load_library(name='libgvhf_rys_b200'):
     lib.B200_set_counter.argtypes = [vp]
     lib.B200_condense.restype = c_int
     lib.B200_condense.argtypes = [vp, vp, c_int, c_int, vp, c_int, vp]
+    lib.B200_dfma_burn.restype = c_int
+    lib.B200_dfma_burn.argtypes = [vp, c_int, c_int, c_int, vp]
     _LIB = lib
     return lib
 

@@ -93,6 +93,11 @@ int B200_qcond(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, i
 int B200_condense(float *out, const double *dm, int n_dm, int nao, const int *ao_loc, int nbas,
                   void *stream);
 
+/* Measurement only: FP64 FMA burn (8 independent chains per thread, `iters`
+ * rounds; 16 flops per thread and round) -- the DFMA-peak denominator of the
+ * roofline is timed with CUDA events around this launch (bench.py). */
+int B200_dfma_burn(double *sink, int iters, int blocks, int threads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
