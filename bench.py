@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: seconds per direct-SCF J/K build (BASELINE.json metric)
+for Taxol / def2-TZVP (2228 spherical AOs, 2538 sorted Cartesian) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full J/K build (`_VHFOpt.get_jk`, hermi=1, n_dm=1): density
+screening (dm_cond), every angular-class launch, the all-reduce of the [J|K]
+partials when N > 1 and the symmetrisation.
+
+  value   : s/build with the (sorted-basis) density resident in HBM, timed with
+            CUDA events on the launching stream, max over ranks
+  e2e     : s/build through the public plugin call `scf.jk.get_jk(mol, dm_host)`
+            with the density in pinned host memory and J, K read back to the host
+            inside the timed region
+  roofline: FP64-FMA bound.  achieved = F_alg / t (F_alg: SURVEY.md 8d flop model
+            x surviving quartets counted by the kernels); peak = DFMA burn
+            measured in this very run (B200_dfma_burn)
+  cpu_baseline: the CPU oracle (oracle/md_jk.c, OpenMP) timed on a fragment of
+            the same molecule and scaled by algorithmic flops
+
+`--impl reference` times only the CPU oracle (PySCF/libcvhf cannot be installed
+here: see DESIGN.md), on the same bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'J/K build s/iter (direct SCF, Taxol def2-TZVP)'
+MOLDIR = os.path.join(ROOT, 'gpu4pyscf_b200', 'data', 'molecules')
+
+
+def decaying_density(mol, seed=0, beta=0.8):
+    '''Synthetic symmetric density with the exponential inter-atomic decay of an
+    insulator's density matrix: D_ab = (u_ab - 1/2) exp(-beta |R_A - R_B|) + delta_ab.'''
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    nao = mol.nao
+    ao_atom = np.repeat(mol._bas[:, 0], np.diff(mol.ao_loc_nr()))
+    R = mol.atom_coords()
+    dist = np.linalg.norm(R[ao_atom][:, None] - R[ao_atom][None], axis=-1)
+    d = (rng.rand(nao, nao) - .5) * np.exp(-beta * dist)
+    return d + d.T + np.eye(nao)
+
+
+def load_mol(name, basis, natoms=None):
+    from gpu4pyscf_b200.gto.mole import M, read_xyz
+    xyz = read_xyz(os.path.join(MOLDIR, name + '.xyz'))
+    if natoms:
+        xyz = '\n'.join(xyz.splitlines()[:natoms])
+    return M(atom=xyz, basis=basis)
+
+
+# ----------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    '''SM clock and throttle reasons sampled DURING the timed region (NVML).'''
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.sm_max,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        try:
+            return int(vis.split(',')[local])
+        except Exception:
+            return local
+    return local
+
+
+# ----------------------------------------------------------------------
+def cpu_oracle_sample(natoms, basis, mol_name, tol=1e-13):
+    '''Time the CPU oracle on the first `natoms` atoms of the workload molecule.
+    Returns (seconds, quartets, threads, nao).'''
+    import numpy as np
+    from oracle import oracle
+    mol = load_mol(mol_name, basis, natoms)
+    dm = decaying_density(mol)
+    t0 = time.time()
+    _, _, n = oracle.get_jk(mol, dm, hermi=1, screen=True, tol=tol, return_count=True)
+    return time.time() - t0, int(n), int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1)), mol.nao, mol
+
+
+def algorithmic_flops(opt, dmt_sorted, n_dm=1):
+    '''One counting build: per-class quartet counts (kernel counter) and live
+    per-class kernel times -> F_alg and the per-class table.'''
+    import torch
+    from gpu4pyscf_b200.lib import loader
+    from gpu4pyscf_b200.scf import flops
+    lib = loader.load_library()
+    counter = torch.zeros(1, dtype=torch.int64, device=dmt_sorted.device)
+    opt.counter = counter
+    lib.B200_set_counter(ctypes.c_void_p(counter.data_ptr()))
+    opt.class_timing = {}
+    opt.get_jk(dmt_sorted, 1)
+    torch.cuda.synchronize()
+    rows = opt.class_timing
+    opt.class_timing = None
+    opt.counter = None
+    lib.B200_set_counter(None)
+    f_alg = 0.
+    table = {}
+    for k, v in rows.items():
+        fl = v[3] * flops.f_quartet(k, n_dm)
+        f_alg += fl
+        a = table.setdefault(k[:4], [0., 0, 0.])
+        a[0] += v[0]
+        a[1] += v[3]
+        a[2] += fl
+    return f_alg, table, len(rows)
+
+
+def dfma_peak(device, lib):
+    '''FP64 FMA peak of this GPU right now (TFLOP/s): best of 5 burns.'''
+    import torch
+    sink = torch.zeros(8, dtype=torch.float64, device=device)
+    blocks, threads, iters = 148 * 8, 256, 1 << 15
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    best = 0.
+    for rep in range(6):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.B200_dfma_burn(ctypes.c_void_p(sink.data_ptr()), iters, blocks, threads, stream)
+        e1.record()
+        e1.synchronize()
+        if rep:
+            best = max(best, 16. * iters * blocks * threads / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+# ----------------------------------------------------------------------
+def run_reference(args, rank):
+    '''CPU arm: PySCF's get_jk is not installable here (no pyscf wheel, no
+    network); the restated CPU oracle is timed instead, on a bounded sample.'''
+    if rank != 0:
+        return
+    times = []
+    n = 0
+    cpu_oracle_sample(2, args.basis, args.mol)       # warm-up: loads the library, spins up OpenMP
+    for _ in range(max(1, min(args.steps, 3))):
+        t, n, threads, nao, _ = cpu_oracle_sample(args.cpu_atoms, args.basis, args.mol)
+        times.append(t)
+    t = sum(times) / len(times)
+    sample = ('first %d atoms of %s/%s (nao %d), %d quartets after Schwarz+density screening at 1e-13; '
+              'value is s per J/K build OF THE SAMPLE (not extrapolated)' % (args.cpu_atoms, args.mol, args.basis, nao, n))
+    out = {
+        'impl': 'reference', 'metric': METRIC, 'value': t, 'unit': 's', 'n_gpus': args.gpus,
+        'steps': len(times), 'warmup': 1, 'ms_per_step': t * 1e3, 'higher_is_better': False,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': '%s RHF/%s direct-SCF J/K build' % (args.mol, args.basis), 'sample': sample},
+        'cpu_baseline': {'value': t, 'unit': 's', 'cores': threads, 'kind': 'port', 'sample': sample,
+                         'quartets_per_s': n / t},
+        'e2e': {'value': t, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--mol', default='113_Taxol')
+    ap.add_argument('--basis', default='def2-tzvp')
+    ap.add_argument('--cpu-atoms', type=int, default=6)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--table', default=None, help='write the per-class table (json) here')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the J/K path has no CPU fallback'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    from gpu4pyscf_b200.scf import jk
+    from gpu4pyscf_b200.lib import loader
+    lib = loader.load_library()
+
+    mol = load_mol(args.mol, args.basis)
+    nao = mol.nao
+    dm_host = decaying_density(mol)
+    opt = jk._VHFOpt(mol).build()
+    nao_s = opt.sorted_mol.nao
+    dm_pinned = torch.as_tensor(dm_host).pin_memory()
+    dmt = dm_pinned.to(dev)
+    dms = opt.apply_coeff_C_mat_CT(dmt.reshape(1, nao, nao)).contiguous()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        return opt.get_jk(dms, 1)
+
+    out_j = torch.empty((nao, nao), dtype=torch.float64).pin_memory()
+    out_k = torch.empty((nao, nao), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        d = dm_pinned.to(dev, non_blocking=True)
+        vj, vk = jk.get_jk(mol, d, hermi=1, vhfopt=opt)
+        out_j.copy_(vj, non_blocking=True)
+        out_k.copy_(vk, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    # ---- warm-up (also compiles nothing: all kernels are prebuilt) ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    peak = dfma_peak(dev, lib)
+
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+
+    # ---- flop accounting + per-class live timing (one extra, untimed build) ----
+    f_alg, table, nlaunch = algorithmic_flops(opt, dms)
+    fl = torch.tensor([f_alg], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(fl)
+    f_alg_total = float(fl.item())
+    kern_ms = sum(a[0] for a in table.values())
+    top = max(table.items(), key=lambda kv: kv[1][0])
+    achieved = f_alg_total / (ms_step * 1e-3) / 1e12          # whole build, all ranks
+    # the rys class kernels are >99% of the step; "dominant kernel" = the class family
+    kern_tf = f_alg / (kern_ms * 1e-3) / 1e12 if kern_ms else 0.
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            t, n, threads, nao_c, cmol = cpu_oracle_sample(args.cpu_atoms, args.basis, args.mol)
+            # F_alg of the sample, counted by the same GPU screening pass
+            copt = jk._VHFOpt(cmol).build()
+            cd = torch.as_tensor(decaying_density(cmol), device=dev)
+            cds = copt.apply_coeff_C_mat_CT(cd.reshape(1, cmol.nao, cmol.nao)).contiguous()
+            f_c, _, _ = algorithmic_flops(copt, cds)
+            cpu = {'value': t * f_alg_total / f_c, 'unit': 's', 'cores': threads, 'kind': 'port',
+                   'sample': 'CPU oracle (oracle/md_jk.c, OpenMP, restated libcvhf-style direct J/K, not PySCF) on the '
+                             'first %d atoms of %s/%s (nao %d, %d quartets) took %.2f s; value = that time x '
+                             'F_alg(full)/F_alg(sample) = x %.1f' % (args.cpu_atoms, args.mol, args.basis, nao_c, n, t,
+                                                                     f_alg_total / f_c),
+                   'sample_seconds': t, 'sample_gflops': f_c / t / 1e9}
+        nbytes = nao * nao * 8
+        out = {
+            'metric': METRIC, 'value': ms_step * 1e-3, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': False,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': '%s RHF/%s direct-SCF J/K build (hermi=1, n_dm=1, direct_scf_tol=1e-13)'
+                                   % (args.mol, args.basis),
+                       'nao': nao, 'nao_sorted_cart': nao_s, 'nbas_sorted': opt.sorted_mol.nbas,
+                       'density': 'synthetic symmetric, exp(-0.8 R_AB/Bohr) decay + identity (no SCF driver in scope)',
+                       'parallelism': 'q-sorted shell-pair lists dealt round-robin over %d rank(s), one all-reduce of [J|K]' % world,
+                       'l2': 'inputs+outputs (D,J,K = %.0f MB) exceed L2; kernels are FP64-compute bound' % (3 * nao_s * nao_s * 8 / 1e6)},
+            'tflops_fp64': achieved,
+            'f_alg': f_alg_total,
+            'roofline': {'bound': 'fp64_fma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': achieved / (peak * world) if peak else None, 'traffic': None,
+                         'peak_source': 'DFMA burn measured in this run on rank 0 (MEASURED_PEAKS.json has no FP64 figure)',
+                         'kernel': 'rys_jk_kernel / rys_jk_thread_kernel class family (%d launches, %.1f ms of the %.1f ms step on rank 0)'
+                                   % (nlaunch, kern_ms, ms_step),
+                       'kernel_achieved': kern_tf,
+                       'top_class': {'class': '(%d%d|%d%d)' % top[0], 'ms': top[1][0], 'quartets': top[1][1],
+                                     'tflops': top[1][2] / (top[1][0] * 1e-3) / 1e12 if top[1][0] else None}},
+            'cpu_baseline': cpu,
+            'e2e': {'value': ms_e2e * 1e-3, 'unit': 's', 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': 2 * nbytes},
+            'gpu_launches': (nlaunch + 1) * args.steps,
+            'clocks': clocks,
+        }
+        print(json.dumps(out), flush=True)
+        if args.table:
+            with open(args.table, 'w') as f:
+                json.dump({'(%d%d|%d%d)' % k: v for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])}, f, indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -57,7 +57,7 @@ int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         return 1;
     }
     int nt = JKT_THREADS;
-    int smem = jk_blk_doubles(NDM, C::NFRS, nt, nt) * 8;
+    int smem = (RysSmem<C::NROOTS>::DOUBLES + jk_blk_doubles(NDM, C::NFRS, nt, nt)) * 8;
     t->nq = nt;
     t->slot_doubles = 0;
     int per_sm = rt_prepare(rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>, smem, nt);

@@ -54,10 +54,12 @@ rys_jk_thread_kernel(JKTask t)
     const bool do_j = t.vj != nullptr;
     const bool do_k = t.vk != nullptr;
 
-    double *blk = smem;
+    double *rys_tab = smem;                          // Rys tables of this NROOTS (rys_roots.cuh)
+    double *blk = smem + RysSmem<NROOTS>::DOUBLES;
     int *blk_ints = (int *)(blk + BLK_INTS);
     double *drs = blk + BLK_DRS;
     uint32_t *queue = (uint32_t *)(blk + BLK_DRS + NDM * NFRS);
+    rys_stage_tables<NROOTS>(rys_tab, t.rys_cheb, t.rys_large, tid, NT);
 
     const int *bas = t.bas;
     const double *env = t.env;
@@ -213,8 +215,8 @@ rys_jk_thread_kernel(JKTask t)
                         const double hz = .5 / zeta, he = .5 / eta;
 #pragma unroll
                         for (int root = 0; root < NROOTS; ++root) {
-                            const double rt_aa = rys_value<NROOTS>(root, x, t.rys_cheb, t.rys_large) * zei;
-                            const double wt = rys_value<NROOTS>(NROOTS + root, x, t.rys_cheb, t.rys_large) * pref;
+                            const double rt_aa = rys_value_s<NROOTS>(root, x, rys_tab) * zei;
+                            const double wt = rys_value_s<NROOTS>(NROOTS + root, x, rys_tab) * pref;
                             const double rt_aij = rt_aa * eta;
                             const double rt_akl = rt_aa * zeta;
                             const double b00 = .5 * rt_aa;

@@ -32,6 +32,7 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct uint3_ { unsigned x, y, z; };
+struct double2 { double x, y; };
 
 extern uint3_ threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
