@@ -4,6 +4,7 @@
 #include "rt.h"
 #include "rys_jk_kernel.cuh"
 #include "rys_jk_thread.cuh"
+#include "rys_jk_warp.cuh"
 
 
 typedef int (*jk_launcher_t)(JKTask *t, int nsm, int smem_max, cudaStream_t stream);
@@ -71,4 +72,52 @@ int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     if (grid < 1) return 0;
     KLAUNCH((rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_thread_kernel");
+}
+
+// warp-team kernel (mid and high classes)
+template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
+int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
+{
+    typedef JKWCfg<LP, LQ, LR, LS, NCS> C;
+    static_assert(C::TW <= 8, "team larger than a 256-thread block");
+    int npq = t->nprim_p * t->nprim_q;
+    int nrs = t->nprim_r * t->nprim_s;
+    if (npq > JK_MAXPP || nrs > JK_MAXPP) {
+        fprintf(stderr, "rys_jk: more than %d primitive pairs per shell pair\n", JK_MAXPP);
+        return 1;
+    }
+    const int nteams = JKW_MAXTHREADS / C::TEAM;
+    const int nt = nteams * C::TEAM;
+    const int nprimq = npq * nrs;
+    // g-sets per lane slot: enough to occupy a warp in the root phase
+    int K = (32 + C::NSW * 2 * C::NROOTS - 1) / (C::NSW * 2 * C::NROOTS);
+    if (K > 4) K = 4;
+    if (K < 1) K = 1;
+    if (nprimq > 1 && K > nprimq) K = nprimq;
+    const int minb = jkw_minblocks(C::TILE, NDM, NCS == 1 ? C::SUBSIZE : LS + 1, C::TEAM);
+    auto smem_of = [&](int k) {
+        return (RysSmem<C::NROOTS>::DOUBLES
+                + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET)) * 8;
+    };
+    const int budget = (smem_max + 1024) / minb - 1024;
+    while (K > 1 && smem_of(K) > budget) --K;
+    int smem = smem_of(K);
+    if (smem > smem_max) {
+        fprintf(stderr, "rys_jk_warp: class (%d%d|%d%d) needs %d B of shared memory\n", LP, LQ, LR, LS, smem);
+        return 1;
+    }
+    t->nq = K;
+    t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET);
+    int per_sm = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM>, smem, nt);
+    if (per_sm < 1) {
+        fprintf(stderr, "rys_jk_warp: class (%d%d|%d%d) cannot be made resident (smem %d, threads %d)\n",
+                LP, LQ, LR, LS, smem, nt);
+        return 1;
+    }
+    int nitems = (t->npair_x + t->world - 1) / t->world;
+    int grid = nsm * per_sm;
+    if (grid * nteams > nitems) grid = (nitems + nteams - 1) / nteams;
+    if (grid < 1) return 0;
+    KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM>), grid, nt, smem, stream, *t);
+    return rt_last_error("rys_jk_warp_kernel");
 }

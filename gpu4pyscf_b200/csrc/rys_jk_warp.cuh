@@ -1,0 +1,619 @@
+// Warp-team variant of the direct-SCF J/K class kernel (sm_100a, FP64).
+//
+// Same arithmetic and output conventions as rys_jk_kernel (rys_jk_kernel.cuh),
+// different execution model: the unit of work is a TEAM of TW warps that owns
+// one X = (r,s) shell pair at a time, screens its own stream of Y = (p,q) pairs
+// (ballot compaction into a private queue) and evaluates NSW quartets at once
+// (TW == 1: lanes = NSW x nf_p*nf_q*NCS; TW > 1: one quartet over TW warps).
+// Teams never synchronise with each other -- the only barriers are __syncwarp
+// (TW == 1) or a named barrier over the team's warps -- so the long dependent
+// chains of the root and recurrence phases of one team overlap the FMA-dense
+// contraction/digestion phases of the other teams resident on the SM.
+//
+// Per pass a team holds NSW*K "g-sets" (roots, weights, 2D integrals of one
+// primitive quartet) in shared memory:
+//   uncontracted class (1 primitive quartet): K different quartets per lane slot
+//   contracted class: K primitive quartets of the same quartet
+// so that the root / VRR+TRR / HRR phases run on NSW*K*{2,3}*NROOTS lanes
+// instead of {2,3}*NROOTS.  The Rys tables of this NROOTS live in shared memory
+// (rys_roots.cuh).
+//
+// Replaces (with rys_jk_kernel for the largest classes) the reference's
+// rys_jk_kernel / rys_k_kernel / unrolled kernels
+// (gpu4pyscf/lib/gvhf-rys/rys_contract_jk.cu:33-333, unrolled_rys_jk.cu) and
+// its task generator _fill_vjk_tasks (create_tasks.cu:113-180).
+#pragma once
+#include "common.cuh"
+#include "rys_roots.cuh"
+#include "rys_jk_kernel.cuh"
+
+template <int LP, int LQ, int LR, int LS, int NCS>
+struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
+    typedef JKCfg<LP, LQ, LR, LS, NCS> B;
+    static constexpr int TW = (B::G + 31) / 32;          // warps per team
+    static constexpr int TEAM = TW * 32;
+    static constexpr int NSW = TW == 1 ? 32 / B::G : 1;  // quartets per team in the contraction phase
+    static constexpr int GSET = (2 * B::NROOTS + 3 * B::NROOTS * (B::G2SIZE + B::GSIZE)) | 1;
+    // registers: gout + J_rs accumulators + one root's gx/gy/gz tile
+    static constexpr int TILE = B::NC * B::NFS;
+};
+
+#define JKW_SLOT_HDR 8       // AB[3], A[3], fac, (p0,q0)
+
+// shared-memory doubles of one team (used by the kernel and by the launcher)
+__host__ __device__ inline int jkw_team_doubles(int team_threads, int nsw, int K, int npq, int nrs,
+                                                int ndm, int nfrs, int gset)
+{
+    int ngs = nsw * K;
+    int nqs = (npq * nrs == 1) ? ngs : nsw;
+    int qcap = nqs + team_threads;
+    int n = 8 + nrs * 5 + ndm * nfrs + (qcap + 1) / 2 + nqs * (JKW_SLOT_HDR + 5 * npq) + ngs * gset;
+    return (n + 1) & ~1;
+}
+
+template <int TW>
+__device__ __forceinline__ void jkw_team_sync(int team)
+{
+#ifdef CPU_EMUL
+    if (TW == 1) __syncwarp();
+    else emul_barrier(1 + team, TW * 32);
+#else
+    if (TW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(TW * 32) : "memory");
+#endif
+}
+
+#ifndef JKW_MAXTHREADS
+#define JKW_MAXTHREADS 256
+#endif
+// resident blocks per SM asked from the register allocator, by register-tile size
+__host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int team)
+{
+    // doubles live in the contraction phase: gout + jacc*ndm + 3*sub
+    int d = tile * (1 + ndm) + 3 * sub;
+    int regs = 2 * d + 48;
+    int threads = (JKW_MAXTHREADS / team) * team;
+    int nb = 65536 / (regs * threads);
+    return nb < 1 ? 1 : (nb > 4 ? 4 : nb);
+}
+
+template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
+__global__ void
+__launch_bounds__((JKW_MAXTHREADS / JKWCfg<LP, LQ, LR, LS, NCS>::TEAM) * JKWCfg<LP, LQ, LR, LS, NCS>::TEAM,
+                  jkw_minblocks(JKWCfg<LP, LQ, LR, LS, NCS>::TILE, NDM,
+                                NCS == 1 ? JKWCfg<LP, LQ, LR, LS, NCS>::SUBSIZE : LS + 1,
+                                JKWCfg<LP, LQ, LR, LS, NCS>::TEAM))
+rys_jk_warp_kernel(JKTask t)
+{
+    typedef JKWCfg<LP, LQ, LR, LS, NCS> C;
+    constexpr int NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS, NFRS = C::NFRS;
+    constexpr int LPQ = C::LPQ, LRS = C::LRS, NROOTS = C::NROOTS;
+    constexpr int G2SIZE = C::G2SIZE, GSIZE = C::GSIZE, NC = C::NC, G = C::G;
+    constexpr int SUB = C::SUBSIZE;
+    constexpr int TW = C::TW, TEAM = C::TEAM, NSW = C::NSW, GSET = C::GSET;
+    constexpr int NAB2 = (LP + 1) * (LQ + 1);
+
+#ifdef CPU_EMUL
+    double *smem = (double *)emul_dynamic_smem;
+#else
+    extern __shared__ double smem[];
+#endif
+    const int tid = threadIdx.x;
+    const int team = tid / TEAM;
+    const int lt = tid - team * TEAM;
+    const int lane = tid & 31;
+
+    double *rys_tab = smem;
+    rys_stage_tables<NROOTS>(rys_tab, t.rys_cheb, t.rys_large, tid, blockDim.x);
+    __syncthreads();
+
+    const int npq = t.nprim_p * t.nprim_q;
+    const int nrs = t.nprim_r * t.nprim_s;
+    const int nprimq = npq * nrs;
+    const bool single = nprimq == 1;
+    const int K = t.nq;                      // g-sets per lane slot
+    const int ngs = NSW * K;
+    const int nqs = single ? ngs : NSW;      // quartets per batch
+    const int qcap = nqs + TEAM;
+    const int slot_d = JKW_SLOT_HDR + 5 * npq;
+    const int npass = single ? 1 : (nprimq + K - 1) / K;
+
+    double *tm = smem + RysSmem<NROOTS>::DOUBLES + team * t.slot_doubles;
+    int *tm_ints = (int *)tm;                // [0] ix, [1] qn, [2] exhausted
+    double *rsgeom = tm + 2;                 // CD[3], C[3]
+    double *rsprim = tm + 8;                 // nrs * 5: eta, Qx, Qy, Qz, coef
+    double *drs = rsprim + nrs * 5;
+    uint32_t *queue = (uint32_t *)(drs + NDM * NFRS);
+    double *slots = drs + NDM * NFRS + (qcap + 1) / 2;
+    double *gsets = slots + nqs * slot_d;
+
+    const int nbas = t.nbas;
+    const int nao = t.nao;
+    const size_t nao2 = (size_t)nao * nao;
+    const bool do_j = t.vj != nullptr;
+    const bool do_k = t.vk != nullptr;
+    const int *bas = t.bas;
+    const double *env = t.env;
+    const int *ao_loc = t.ao_loc;
+
+    // contraction-phase role of this lane
+    const int s4 = (TW == 1) ? lane / G : 0;
+    const bool lane_on = (TW == 1) ? (s4 < NSW) : (lt < G);
+    const int tg = lane_on ? ((TW == 1) ? lane - s4 * G : lt) : 0;
+    const int ab = tg / NCS;
+    const int cpart = tg - ab * NCS;
+    const int a = ab / NFQ;
+    const int b = ab - a * NFQ;
+    const int c0 = cpart * NC;
+    const int gbx = (cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * SUB;
+    const int gby = (cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * SUB + GSIZE;
+    const int gbz = (cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * SUB + 2 * GSIZE;
+    int ox[NC], oy[NC], oz[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        int c = c0 + n;
+        if (c >= NFR) c = NFR - 1;
+        ox[n] = cart_x(LR, c) * (LS + 1);
+        oy[n] = cart_y(LR, c) * (LS + 1);
+        oz[n] = cart_z(LR, c) * (LS + 1);
+    }
+
+    while (true) {
+        // ---------------- next X pair of this team ----------------
+        jkw_team_sync<TW>(team);
+        if (lt == 0) {
+            tm_ints[0] = atomicAdd(t.head, 1) * t.world + t.rank;
+            tm_ints[1] = 0;
+            tm_ints[2] = 0;
+        }
+        jkw_team_sync<TW>(team);
+        const int ix = tm_ints[0];
+        if (ix >= t.npair_x) break;
+        const uint32_t pair_rs = t.pair_x[ix];
+        const int rsh = pair_rs / nbas;
+        const int ssh = pair_rs - rsh * nbas;
+        const int r0 = ao_loc[rsh];
+        const int s0 = ao_loc[ssh];
+        const float thr = t.cutoff - t.q_x[ix];
+        {
+            const double *Rr = env + bas[rsh * BAS_SLOTS + PTR_BAS_COORD];
+            const double *Rs = env + bas[ssh * BAS_SLOTS + PTR_BAS_COORD];
+            const double *er = env + bas[rsh * BAS_SLOTS + PTR_EXP];
+            const double *es = env + bas[ssh * BAS_SLOTS + PTR_EXP];
+            const double *cr = env + bas[rsh * BAS_SLOTS + PTR_COEFF];
+            const double *cs = env + bas[ssh * BAS_SLOTS + PTR_COEFF];
+            double dx = Rr[0] - Rs[0], dy = Rr[1] - Rs[1], dz = Rr[2] - Rs[2];
+            double rr2 = dx * dx + dy * dy + dz * dz;
+            for (int i = lt; i < nrs; i += TEAM) {
+                int ir = i / t.nprim_s;
+                int is = i - ir * t.nprim_s;
+                double ar = er[ir], as = es[is];
+                double eta = ar + as;
+                double f = as / eta;
+                double *o = rsprim + i * 5;
+                o[0] = eta;
+                o[1] = Rr[0] - f * dx;
+                o[2] = Rr[1] - f * dy;
+                o[3] = Rr[2] - f * dz;
+                o[4] = cr[ir] * cs[is] * exp(-ar * f * rr2);
+            }
+            if (lt < 3) {
+                rsgeom[lt] = Rr[lt] - Rs[lt];
+                rsgeom[3 + lt] = Rr[lt];
+            }
+            for (int i = lt; i < NDM * NFRS; i += TEAM) {
+                int idm = i / NFRS;
+                int cd = i - idm * NFRS;
+                int c = cd / NFS;
+                int d = cd - c * NFS;
+                drs[i] = t.dm[idm * nao2 + (size_t)(r0 + c) * nao + s0 + d];
+            }
+        }
+        double jacc[NDM][NC][NFS];
+#pragma unroll
+        for (int idm = 0; idm < NDM; ++idm)
+#pragma unroll
+            for (int n = 0; n < NC; ++n)
+#pragma unroll
+                for (int d = 0; d < NFS; ++d) jacc[idm][n][d] = 0.;
+
+        int ypos = (t.dedupe == 1) ? ix : 0;
+        const float *dc_r = t.dm_cond + (size_t)rsh * nbas;
+        const float *dc_s = t.dm_cond + (size_t)ssh * nbas;
+        const float d_rs = dc_r[ssh];
+        int qn = 0;
+        int exhausted = 0;
+        jkw_team_sync<TW>(team);
+
+        while (true) {
+            // ---------------- screen Y pairs into the team queue ----------------
+            while (!exhausted && qn < nqs) {
+                const int y = ypos + lt;
+                bool keep = false, stop = false;
+                if (y >= t.npair_y) {
+                    stop = true;
+                } else {
+                    float qy = t.q_y[y];
+                    if (qy + t.dm_penalty + t.q_margin < thr) {
+                        stop = true;                  // sorted: nothing further survives
+                    } else {
+                        uint32_t pair_pq = t.pair_y[y];
+                        int psh = pair_pq / nbas;
+                        int qsh = pair_pq - psh * nbas;
+                        keep = qy + t.dm_penalty >= thr;
+                        if (t.dedupe == 2) keep = keep && pair_rs >= pair_pq;
+                        if (t.dedupe == 3) keep = keep && pair_pq >= pair_rs;
+                        if (keep) {
+                            const float *dc_p = t.dm_cond + (size_t)psh * nbas;
+                            float dmax = -1e30f;
+                            if (do_j) dmax = fmaxf(d_rs, dc_p[qsh]);
+                            if (do_k) {
+                                dmax = fmaxf(dmax, fmaxf(dc_r[psh], dc_r[qsh]));
+                                dmax = fmaxf(dmax, fmaxf(dc_s[psh], dc_s[qsh]));
+                            }
+                            keep = dmax + qy > thr;
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int cnt = __popc(m);
+                int base = qn;
+                if (TW > 1) {
+                    base = 0;
+                    if (lane == 0 && cnt) base = atomicAdd(&tm_ints[1], cnt);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                }
+                if (keep) queue[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)y;
+                if (TW == 1) {
+                    qn += cnt;
+                    exhausted = __any_sync(0xffffffffu, stop);
+                    __syncwarp();
+                } else {
+                    if (stop) tm_ints[2] = 1;
+                    jkw_team_sync<TW>(team);
+                    qn = tm_ints[1];
+                    exhausted = tm_ints[2];
+                    jkw_team_sync<TW>(team);
+                }
+                ypos += TEAM;
+            }
+            if (qn == 0) break;                       // exhausted and nothing queued
+            const int nb = qn < nqs ? qn : nqs;
+
+            // ---------------- quartet slots: Gaussian products of the Y pairs ----------------
+            for (int i = lt; i < nqs * npq; i += TEAM) {
+                const int j = i / npq;
+                const int ip = i - j * npq;
+                const bool active = j < nb;
+                const int iy = queue[active ? j : 0];
+                const uint32_t pair_pq = t.pair_y[iy];
+                const int psh = pair_pq / nbas;
+                const int qsh = pair_pq - psh * nbas;
+                const double *Rp = env + bas[psh * BAS_SLOTS + PTR_BAS_COORD];
+                const double *Rq = env + bas[qsh * BAS_SLOTS + PTR_BAS_COORD];
+                const double *ep = env + bas[psh * BAS_SLOTS + PTR_EXP];
+                const double *eq = env + bas[qsh * BAS_SLOTS + PTR_EXP];
+                const double *cp = env + bas[psh * BAS_SLOTS + PTR_COEFF];
+                const double *cq = env + bas[qsh * BAS_SLOTS + PTR_COEFF];
+                double dx = Rp[0] - Rq[0], dy = Rp[1] - Rq[1], dz = Rp[2] - Rq[2];
+                double rr2 = dx * dx + dy * dy + dz * dz;
+                const int ipp = ip / t.nprim_q;
+                const int iq = ip - ipp * t.nprim_q;
+                double ap = ep[ipp], aq = eq[iq];
+                double zeta = ap + aq;
+                double f = aq / zeta;
+                double *sl = slots + j * slot_d;
+                double *o = sl + JKW_SLOT_HDR + ip * 5;
+                o[0] = zeta;
+                o[1] = Rp[0] - f * dx;
+                o[2] = Rp[1] - f * dy;
+                o[3] = Rp[2] - f * dz;
+                o[4] = cp[ipp] * cq[iq] * exp(-ap * f * rr2);
+                if (ip == 0) {
+                    sl[0] = dx; sl[1] = dy; sl[2] = dz;
+                    sl[3] = Rp[0]; sl[4] = Rp[1]; sl[5] = Rp[2];
+                    double fac = PI_FAC;
+                    if (psh == qsh) fac *= .5;
+                    if (rsh == ssh) fac *= .5;
+                    if (pair_pq == pair_rs) fac *= .5;
+                    sl[6] = active ? fac : 0.;
+                    int *pi = (int *)(sl + 7);
+                    pi[0] = ao_loc[psh];
+                    pi[1] = ao_loc[qsh];
+                }
+            }
+            double gout[NC][NFS];
+#pragma unroll
+            for (int n = 0; n < NC; ++n)
+#pragma unroll
+                for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
+            jkw_team_sync<TW>(team);
+
+            for (int pass = 0; pass < npass; ++pass) {
+                // ---------------- phase 1: roots and weights of every g-set ----------------
+                for (int it = lt; it < ngs * 2 * NROOTS; it += TEAM) {
+                    const int g = it / (2 * NROOTS);
+                    const int idx = it - g * (2 * NROOTS);
+                    int j = g, pi = 0;
+                    if (!single) {
+                        const int k = g / NSW;
+                        j = g - k * NSW;
+                        pi = pass * K + k;
+                    }
+                    const bool valid = pi < nprimq;
+                    if (!valid) pi = 0;
+                    const int ipq = pi / nrs;
+                    const int irs = pi - ipq * nrs;
+                    const double *sl = slots + j * slot_d;
+                    const double *pp = sl + JKW_SLOT_HDR + ipq * 5;
+                    const double *rr = rsprim + irs * 5;
+                    double zeta = pp[0], eta = rr[0];
+                    double dx = pp[1] - rr[1], dy = pp[2] - rr[2], dz = pp[3] - rr[3];
+                    double ze = zeta + eta;
+                    double x = zeta * eta / ze * (dx * dx + dy * dy + dz * dz);
+                    double v = rys_value_s<NROOTS>(idx, x, rys_tab);
+                    double *rw = gsets + g * GSET;
+                    if (idx < NROOTS) {
+                        rw[idx] = v / ze;
+                    } else {
+                        double w = valid ? sl[6] * pp[4] * rr[4] / (zeta * eta * sqrt(ze)) : 0.;
+                        rw[idx] = v * w;
+                    }
+                }
+                jkw_team_sync<TW>(team);
+                // ---------------- phase 2: VRR + TRR, one (g-set, root, axis) per lane ----------------
+                for (int it = lt; it < ngs * 3 * NROOTS; it += TEAM) {
+                    const int g = it / (3 * NROOTS);
+                    const int ra = it - g * (3 * NROOTS);
+                    const int root = ra / 3;
+                    const int axis = ra - root * 3;
+                    int j = g, pi = 0;
+                    if (!single) {
+                        const int k = g / NSW;
+                        j = g - k * NSW;
+                        pi = pass * K + k;
+                        if (pi >= nprimq) pi = 0;
+                    }
+                    const int ipq = pi / nrs;
+                    const int irs = pi - ipq * nrs;
+                    const double *sl = slots + j * slot_d;
+                    const double *pp = sl + JKW_SLOT_HDR + ipq * 5;
+                    const double *rr = rsprim + irs * 5;
+                    double *gs = gsets + g * GSET;
+                    double zeta = pp[0], eta = rr[0];
+                    double rt_aa = gs[root];
+                    double rt_aij = rt_aa * eta;
+                    double rt_akl = rt_aa * zeta;
+                    double b00 = .5 * rt_aa;
+                    double b10 = .5 / zeta * (1. - rt_aij);
+                    double b01 = .5 / eta * (1. - rt_akl);
+                    double P = pp[1 + axis], Q = rr[1 + axis];
+                    double PQ = P - Q;
+                    double c0p = (P - sl[3 + axis]) - rt_aij * PQ;
+                    double cpq = (Q - rsgeom[3 + axis]) + rt_akl * PQ;
+                    double gg[LRS + 1][LPQ + 1];
+                    gg[0][0] = (axis == 2) ? gs[NROOTS + root] : 1.;
+                    if (LPQ > 0) {
+                        gg[0][1] = c0p * gg[0][0];
+#pragma unroll
+                        for (int e = 1; e < LPQ; ++e)
+                            gg[0][e + 1] = c0p * gg[0][e] + e * b10 * gg[0][e - 1];
+                    }
+                    if (LRS > 0) {
+                        gg[1][0] = cpq * gg[0][0];
+#pragma unroll
+                        for (int e = 1; e <= LPQ; ++e)
+                            gg[1][e] = cpq * gg[0][e] + e * b00 * gg[0][e - 1];
+#pragma unroll
+                        for (int f = 1; f < LRS; ++f) {
+                            gg[f + 1][0] = cpq * gg[f][0] + f * b01 * gg[f - 1][0];
+#pragma unroll
+                            for (int e = 1; e <= LPQ; ++e)
+                                gg[f + 1][e] = cpq * gg[f][e] + f * b01 * gg[f - 1][e] + e * b00 * gg[f][e - 1];
+                        }
+                    }
+                    double *o = gs + 2 * NROOTS + ra * G2SIZE;
+#pragma unroll
+                    for (int f = 0; f <= LRS; ++f)
+#pragma unroll
+                        for (int e = 0; e <= LPQ; ++e) o[f * (LPQ + 1) + e] = gg[f][e];
+                }
+                jkw_team_sync<TW>(team);
+                // ---------------- phase 3: HRR (bra then ket), one (g-set, root, axis, ea, eb) per lane ----------------
+                for (int it = lt; it < ngs * 3 * NROOTS * NAB2; it += TEAM) {
+                    const int g = it / (3 * NROOTS * NAB2);
+                    const int r3 = it - g * (3 * NROOTS * NAB2);
+                    const int ra = r3 / NAB2;
+                    const int ab2 = r3 - ra * NAB2;
+                    const int ea = ab2 / (LQ + 1);
+                    const int eb = ab2 - ea * (LQ + 1);
+                    const int axis = ra % 3;
+                    const int j = single ? g : g % NSW;
+                    const double AB = slots[j * slot_d + axis];
+                    const double CD = rsgeom[axis];
+                    double *gs = gsets + g * GSET;
+                    const double *in = gs + 2 * NROOTS + ra * G2SIZE + ea;
+                    double v[LRS + 1];
+#pragma unroll
+                    for (int f = 0; f <= LRS; ++f) {
+                        double u[LQ + 1];
+#pragma unroll
+                        for (int e = 0; e <= LQ; ++e) u[e] = (e <= eb) ? in[f * (LPQ + 1) + e] : 0.;
+#pragma unroll
+                        for (int k = 0; k < LQ; ++k) {
+                            if (k < eb) {
+#pragma unroll
+                                for (int e = 0; e < LQ - k; ++e) u[e] = u[e + 1] + AB * u[e];
+                            }
+                        }
+                        v[f] = u[0];
+                    }
+                    double *o = gs + 2 * NROOTS + 3 * NROOTS * G2SIZE + ra * GSIZE + ab2 * SUB;
+#pragma unroll
+                    for (int d = 0; d <= LS; ++d) {
+#pragma unroll
+                        for (int c = 0; c <= LR; ++c) o[c * (LS + 1) + d] = v[c];
+                        if (d < LS) {
+#pragma unroll
+                            for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                        }
+                    }
+                }
+                jkw_team_sync<TW>(team);
+                // ---------------- phase 4: gout += gx * gy * gz ; digestion ----------------
+                for (int k = 0; k < K; ++k) {
+                    const double *gk = gsets + (k * NSW + s4) * GSET + 2 * NROOTS + 3 * NROOTS * G2SIZE;
+                    if (lane_on) {
+                        if (NCS == 1) {
+#pragma unroll
+                            for (int root = 0; root < NROOTS; ++root) {
+                                const double *gr = gk + root * 3 * GSIZE;
+                                double gx[SUB], gy[SUB], gz[SUB];
+#pragma unroll
+                                for (int i = 0; i < SUB; ++i) {
+                                    gx[i] = gr[gbx + i];
+                                    gy[i] = gr[gby + i];
+                                    gz[i] = gr[gbz + i];
+                                }
+#pragma unroll
+                                for (int c = 0; c < NFR; ++c) {
+#pragma unroll
+                                    for (int d = 0; d < NFS; ++d) {
+                                        gout[c][d] += gx[cart_x(LR, c) * (LS + 1) + cart_x(LS, d)]
+                                                    * gy[cart_y(LR, c) * (LS + 1) + cart_y(LS, d)]
+                                                    * gz[cart_z(LR, c) * (LS + 1) + cart_z(LS, d)];
+                                    }
+                                }
+                            }
+                        } else {
+                            for (int root = 0; root < NROOTS; ++root) {
+                                const double *gr = gk + root * 3 * GSIZE;
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) {
+                                    double gx[LS + 1], gy[LS + 1], gz[LS + 1];
+#pragma unroll
+                                    for (int i = 0; i <= LS; ++i) {
+                                        gx[i] = gr[gbx + ox[n] + i];
+                                        gy[i] = gr[gby + oy[n] + i];
+                                        gz[i] = gr[gbz + oz[n] + i];
+                                    }
+#pragma unroll
+                                    for (int d = 0; d < NFS; ++d) {
+                                        gout[n][d] += gx[cart_x(LS, d)] * gy[cart_y(LS, d)] * gz[cart_z(LS, d)];
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    const bool dig = single || (pass == npass - 1 && k == K - 1);
+                    if (!dig) continue;
+                    const int j = single ? k * NSW + s4 : s4;
+                    if (lane_on && j < nb) {
+                        const double *sl = slots + j * slot_d;
+                        const int *pi = (const int *)(sl + 7);
+                        const int p0 = pi[0];
+                        const int q0 = pi[1];
+                        const size_t prow = (size_t)(p0 + a) * nao;
+                        const size_t qrow = (size_t)(q0 + b) * nao;
+#pragma unroll
+                        for (int idm = 0; idm < NDM; ++idm) {
+                            const double *dm = t.dm + idm * nao2;
+                            if (do_j) {
+                                double *vj = t.vj + idm * nao2;
+                                double dpq = dm[prow + q0 + b];
+                                double s = 0.;
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) {
+                                    if (c0 + n < NFR) {
+#pragma unroll
+                                        for (int d = 0; d < NFS; ++d) {
+                                            s += gout[n][d] * drs[idm * NFRS + (c0 + n) * NFS + d];
+                                            jacc[idm][n][d] += gout[n][d] * dpq;
+                                        }
+                                    }
+                                }
+                                JK_ATOMIC_ADD(vj + prow + q0 + b, s);
+                            }
+                            if (do_k) {
+                                double *vk = t.vk + idm * nao2;
+                                double dqs[NFS], dps[NFS], kps[NFS], kqs[NFS];
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) {
+                                    dqs[d] = dm[qrow + s0 + d];
+                                    dps[d] = dm[prow + s0 + d];
+                                    kps[d] = 0.;
+                                    kqs[d] = 0.;
+                                }
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) {
+                                    if (c0 + n < NFR) {
+                                        double dqr = dm[qrow + r0 + c0 + n];
+                                        double dpr = dm[prow + r0 + c0 + n];
+                                        double kpr = 0., kqr = 0.;
+#pragma unroll
+                                        for (int d = 0; d < NFS; ++d) {
+                                            double gv = gout[n][d];
+                                            kpr += gv * dqs[d];
+                                            kqr += gv * dps[d];
+                                            kps[d] += gv * dqr;
+                                            kqs[d] += gv * dpr;
+                                        }
+                                        JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr);
+                                        JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr);
+                                    }
+                                }
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) {
+                                    JK_ATOMIC_ADD(vk + prow + s0 + d, kps[d]);
+                                    JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int n = 0; n < NC; ++n)
+#pragma unroll
+                        for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
+                }
+            }   // passes
+
+            // ---------------- keep the unprocessed remainder of the queue ----------------
+            jkw_team_sync<TW>(team);
+            if (lt == 0 && t.counter != nullptr) atomicAdd(t.counter, (unsigned long long)nb);
+            const int rem = qn - nb;
+            uint32_t keepv = 0;
+            if (lt < rem) keepv = queue[nb + lt];
+            jkw_team_sync<TW>(team);
+            if (lt < rem) queue[lt] = keepv;
+            qn = rem;
+            if (TW > 1) {
+                if (lt == 0) tm_ints[1] = rem;
+            }
+            jkw_team_sync<TW>(team);
+            if (exhausted && qn == 0) break;
+        }
+
+        // ---------------- flush J_rs ----------------
+        if (do_j) {
+#pragma unroll
+            for (int idm = 0; idm < NDM; ++idm) {
+                double *vj = t.vj + idm * nao2;
+#pragma unroll
+                for (int n = 0; n < NC; ++n) {
+#pragma unroll
+                    for (int d = 0; d < NFS; ++d) {
+                        double v = jacc[idm][n][d];
+                        if (TW == 1 && NCS == 1) {
+                            // every lane holds a partial sum of the same (c,d): butterfly, one atomic per warp
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            if (lane == 0 && v != 0.) JK_ATOMIC_ADD(vj + (size_t)(r0 + n) * nao + s0 + d, v);
+                        } else if (lane_on && c0 + n < NFR && v != 0.) {
+                            JK_ATOMIC_ADD(vj + (size_t)(r0 + c0 + n) * nao + s0 + d, v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}

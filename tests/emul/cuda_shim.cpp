@@ -25,6 +25,26 @@ void trampoline()
 }
 }
 
+double emul_xchg[64][32];
+namespace {
+struct Bar { int count; int gen; };
+Bar bars[128];
+}
+
+// counting barrier over `nthreads` fibers; arrivals after the last one wait for
+// the generation to advance (all participants must call with the same id/count)
+void emul_barrier(int id, int nthreads)
+{
+    Bar &b = bars[id];
+    int g = b.gen;
+    if (++b.count >= nthreads) {
+        b.count = 0;
+        b.gen++;
+        return;
+    }
+    while (b.gen == g) emul_yield();
+}
+
 void emul_yield()
 {
     swapcontext(&fibers[current].ctx, &sched_ctx);
@@ -33,6 +53,7 @@ void emul_yield()
 void emul_run_block(std::function<void()> body, unsigned nthreads)
 {
     cur_body = &body;
+    memset(bars, 0, sizeof(bars));
     if (fibers.size() < nthreads) {
         size_t old = fibers.size();
         fibers.resize(nthreads);

@@ -45,8 +45,48 @@ typedef void *cudaStream_t;
 void emul_yield();
 void emul_run_block(std::function<void()> body, unsigned nthreads);
 
-static inline void __syncthreads() { emul_yield(); }
-static inline void __syncwarp(unsigned = 0xffffffff) {}
+// barriers: id 0 = whole block, 1..15 = named (team) barriers, 64+w = warp w
+void emul_barrier(int id, int nthreads);
+extern double emul_xchg[64][32];
+static inline int emul_warp_threads()
+{
+    int nt = blockDim.x, w = threadIdx.x >> 5;
+    return nt - w * 32 < 32 ? nt - w * 32 : 32;
+}
+static inline void __syncthreads() { emul_barrier(0, blockDim.x); }
+static inline void __syncwarp(unsigned = 0xffffffff) { emul_barrier(64 + (threadIdx.x >> 5), emul_warp_threads()); }
+template <class T> static inline T emul_shfl(T v, int src)
+{
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (src < 0 || src >= emul_warp_threads()) src = lane;
+    memcpy(&emul_xchg[w][lane], &v, sizeof(T));
+    __syncwarp();
+    T r;
+    memcpy(&r, &emul_xchg[w][src], sizeof(T));
+    __syncwarp();
+    return r;
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emul_shfl(v, src); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emul_shfl(v, (int)(threadIdx.x & 31) + d); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emul_shfl(v, (int)(threadIdx.x & 31) ^ m); }
+static inline unsigned __ballot_sync(unsigned, bool pred)
+{
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long p = pred ? 1 : 0;
+    memcpy(&emul_xchg[w][lane], &p, 8);
+    __syncwarp();
+    unsigned m = 0;
+    for (int i = 0; i < emul_warp_threads(); ++i) {
+        long long q;
+        memcpy(&q, &emul_xchg[w][i], 8);
+        if (q) m |= 1u << i;
+    }
+    __syncwarp();
+    return m;
+}
+static inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
