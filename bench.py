@@ -36,6 +36,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = 'J/K build s/iter (direct SCF, Taxol def2-TZVP)'
+# F_alg of one full build (SURVEY.md 8d flop model x quartets counted by the GPU
+# kernels for the bench density; profiles/bench_r1_baseline.json).  Only used to
+# scale the CPU arm's bounded sample to the full workload.
+F_ALG_FULL = {('113_Taxol', 'def2-tzvp'): 4.9499377e13}
 MOLDIR = os.path.join(ROOT, 'gpu4pyscf_b200', 'data', 'molecules')
 
 
@@ -128,7 +132,8 @@ def cpu_oracle_sample(natoms, basis, mol_name, tol=1e-13):
     dm = decaying_density(mol)
     t0 = time.time()
     _, _, n = oracle.get_jk(mol, dm, hermi=1, screen=True, tol=tol, return_count=True)
-    return time.time() - t0, int(n), int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1)), mol.nao, mol
+    dt = time.time() - t0
+    return dt, int(n), int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1)), mol.nao, oracle.last_flops()
 
 
 def algorithmic_flops(opt, dmt_sorted, n_dm=1):
@@ -186,22 +191,27 @@ def run_reference(args, rank):
     if rank != 0:
         return
     times = []
-    n = 0
     cpu_oracle_sample(2, args.basis, args.mol)       # warm-up: loads the library, spins up OpenMP
     for _ in range(max(1, min(args.steps, 3))):
-        t, n, threads, nao, _ = cpu_oracle_sample(args.cpu_atoms, args.basis, args.mol)
+        t, n, threads, nao, f_c = cpu_oracle_sample(args.cpu_atoms, args.basis, args.mol)
         times.append(t)
     t = sum(times) / len(times)
-    sample = ('first %d atoms of %s/%s (nao %d), %d quartets after Schwarz+density screening at 1e-13; '
-              'value is s per J/K build OF THE SAMPLE (not extrapolated)' % (args.cpu_atoms, args.mol, args.basis, nao, n))
+    f_full = F_ALG_FULL.get((args.mol, args.basis.lower()))
+    scale = f_full / f_c if f_full else 1.
+    sample = ('CPU oracle (oracle/md_jk.c, OpenMP; restated libcvhf-style direct J/K, PySCF itself is not installable '
+              'here) on the first %d atoms of %s/%s (nao %d, %d quartets after Schwarz+density screening at 1e-13, '
+              'F_alg %.3e) took %.2f s per build; value = that time x F_alg(full build)/F_alg(sample) = x %.1f'
+              % (args.cpu_atoms, args.mol, args.basis, nao, n, f_c, t, scale))
+    v = t * scale
     out = {
-        'impl': 'reference', 'metric': METRIC, 'value': t, 'unit': 's', 'n_gpus': args.gpus,
-        'steps': len(times), 'warmup': 1, 'ms_per_step': t * 1e3, 'higher_is_better': False,
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 's', 'n_gpus': args.gpus,
+        'steps': len(times), 'warmup': 1, 'ms_per_step': v * 1e3, 'higher_is_better': False,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': '%s RHF/%s direct-SCF J/K build' % (args.mol, args.basis), 'sample': sample},
-        'cpu_baseline': {'value': t, 'unit': 's', 'cores': threads, 'kind': 'port', 'sample': sample,
-                         'quartets_per_s': n / t},
-        'e2e': {'value': t, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'config': {'workload': '%s RHF/%s direct-SCF J/K build (hermi=1, n_dm=1, direct_scf_tol=1e-13)'
+                               % (args.mol, args.basis), 'extrapolated_from_sample': bool(f_full)},
+        'cpu_baseline': {'value': v, 'unit': 's', 'cores': threads, 'kind': 'port', 'sample': sample,
+                         'sample_seconds': t, 'sample_gflops': f_c / t / 1e9},
+        'e2e': {'value': v, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(out), flush=True)
 
@@ -313,16 +323,11 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu:
-            t, n, threads, nao_c, cmol = cpu_oracle_sample(args.cpu_atoms, args.basis, args.mol)
-            # F_alg of the sample, counted by the same GPU screening pass
-            copt = jk._VHFOpt(cmol).build()
-            cd = torch.as_tensor(decaying_density(cmol), device=dev)
-            cds = copt.apply_coeff_C_mat_CT(cd.reshape(1, cmol.nao, cmol.nao)).contiguous()
-            f_c, _, _ = algorithmic_flops(copt, cds)
+            t, n, threads, nao_c, f_c = cpu_oracle_sample(args.cpu_atoms, args.basis, args.mol)
             cpu = {'value': t * f_alg_total / f_c, 'unit': 's', 'cores': threads, 'kind': 'port',
                    'sample': 'CPU oracle (oracle/md_jk.c, OpenMP, restated libcvhf-style direct J/K, not PySCF) on the '
-                             'first %d atoms of %s/%s (nao %d, %d quartets) took %.2f s; value = that time x '
-                             'F_alg(full)/F_alg(sample) = x %.1f' % (args.cpu_atoms, args.mol, args.basis, nao_c, n, t,
+                             'first %d atoms of %s/%s (nao %d, %d quartets, F_alg %.3e) took %.2f s; value = that time x '
+                             'F_alg(full)/F_alg(sample) = x %.1f' % (args.cpu_atoms, args.mol, args.basis, nao_c, n, f_c, t,
                                                                      f_alg_total / f_c),
                    'sample_seconds': t, 'sample_gflops': f_c / t / 1e9}
         nbytes = nao * nao * 8
@@ -348,7 +353,7 @@ def main():
                                      'tflops': top[1][2] / (top[1][0] * 1e-3) / 1e12 if top[1][0] else None}},
             'cpu_baseline': cpu,
             'e2e': {'value': ms_e2e * 1e-3, 'unit': 's', 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': 2 * nbytes},
-            'gpu_launches': (nlaunch + 1) * args.steps,
+            'gpu_launches': (nlaunch + 1) * args.steps,   # class kernels + condense per build
             'clocks': clocks,
         }
         print(json.dumps(out), flush=True)

@@ -79,6 +79,16 @@ int cuda_version(void)
 
 static inline int nf_of(int l) { return (l + 1) * (l + 2) / 2; }
 
+// 1 if a kernel is instantiated for lanes = (lp,lq) pairs, register tile = (lr,ls)
+// pairs.  Exactly one orientation of every unordered class exists
+// (tools/gen_instances.py picks it); callers try (Y,X) and swap when it is 0.
+int B200_has_class(int lp, int lq, int lr, int ls)
+{
+    if (lp < 0 || lq < 0 || lr < 0 || ls < 0) return 0;
+    if (lp > LMAX_B200 || lq > LMAX_B200 || lr > LMAX_B200 || ls > LMAX_B200) return 0;
+    return jk_find_launcher(lp, lq, lr, ls, 1) != nullptr;
+}
+
 int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
                         const RysIntEnvVars *envs, const int *lprim,
                         const uint32_t *pair_x, const float *q_x, int npair_x,
@@ -165,10 +175,8 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
 #else
     cudaMemsetAsync(head, 0, sizeof(int), 0);
 #endif
-    // orientation: the pair with more Cartesian components is the register tile (X)
-    bool kl_is_x = nf_of(lk) * nf_of(ll) > nf_of(li) * nf_of(lj)
-                || (nf_of(lk) * nf_of(ll) == nf_of(li) * nf_of(lj) && lk * 8 + ll >= li * 8 + lj);
-    // the tile side must also be the side with li >= lj ordering of the instantiation list
+    // orientation: whichever of (ij|kl) / (kl|ij) is instantiated (B200_has_class)
+    bool kl_is_x = B200_has_class(li, lj, lk, ll);
     if (kl_is_x) {
         int lprim[8] = {li, lj, lk, ll, ni, nj, nk, nl};
         return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,

@@ -110,7 +110,7 @@ rys_jk_thread_kernel(JKTask t)
                 int cd = i - idm * NFRS;
                 int c = cd / NFS;
                 int d = cd - c * NFS;
-                drs[i] = t.dm[idm * nao2 + (size_t)(r0 + c) * nao + s0 + d];
+                drs[i] = __ldg(t.dm + idm * nao2 + (size_t)(r0 + c) * nao + s0 + d);
             }
         }
         double jacc[NDM][NFRS];
@@ -316,7 +316,7 @@ rys_jk_thread_kernel(JKTask t)
                         for (int a = 0; a < NFP; ++a)
 #pragma unroll
                         for (int b = 0; b < NFQ; ++b) {
-                            const double dpq = dm[(size_t)(p0 + a) * nao + q0 + b];
+                            const double dpq = __ldg(dm + (size_t)(p0 + a) * nao + q0 + b);
                             double s = 0.;
 #pragma unroll
                             for (int cd = 0; cd < NFRS; ++cd) {
@@ -334,9 +334,9 @@ rys_jk_thread_kernel(JKTask t)
 #pragma unroll
                         for (int b = 0; b < NFQ; ++b) {
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c) dqr[b][c] = dm[(size_t)(q0 + b) * nao + r0 + c];
+                            for (int c = 0; c < NFR; ++c) dqr[b][c] = __ldg(dm + (size_t)(q0 + b) * nao + r0 + c);
 #pragma unroll
-                            for (int d = 0; d < NFS; ++d) dqs[b][d] = dm[(size_t)(q0 + b) * nao + s0 + d];
+                            for (int d = 0; d < NFS; ++d) dqs[b][d] = __ldg(dm + (size_t)(q0 + b) * nao + s0 + d);
                         }
 #pragma unroll
                         for (int a = 0; a < NFP; ++a) {
@@ -364,9 +364,9 @@ rys_jk_thread_kernel(JKTask t)
 #pragma unroll
                         for (int a = 0; a < NFP; ++a) {
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c) dpr[a][c] = dm[(size_t)(p0 + a) * nao + r0 + c];
+                            for (int c = 0; c < NFR; ++c) dpr[a][c] = __ldg(dm + (size_t)(p0 + a) * nao + r0 + c);
 #pragma unroll
-                            for (int d = 0; d < NFS; ++d) dps[a][d] = dm[(size_t)(p0 + a) * nao + s0 + d];
+                            for (int d = 0; d < NFS; ++d) dps[a][d] = __ldg(dm + (size_t)(p0 + a) * nao + s0 + d);
                         }
 #pragma unroll
                         for (int b = 0; b < NFQ; ++b) {

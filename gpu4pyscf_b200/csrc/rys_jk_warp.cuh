@@ -206,7 +206,7 @@ rys_jk_warp_kernel(JKTask t)
                 int cd = i - idm * NFRS;
                 int c = cd / NFS;
                 int d = cd - c * NFS;
-                drs[i] = t.dm[idm * nao2 + (size_t)(r0 + c) * nao + s0 + d];
+                drs[i] = __ldg(t.dm + idm * nao2 + (size_t)(r0 + c) * nao + s0 + d);
             }
         }
         double jacc[NDM][NC][NFS];
@@ -520,7 +520,7 @@ rys_jk_warp_kernel(JKTask t)
                             const double *dm = t.dm + idm * nao2;
                             if (do_j) {
                                 double *vj = t.vj + idm * nao2;
-                                double dpq = dm[prow + q0 + b];
+                                double dpq = __ldg(dm + prow + q0 + b);
                                 double s = 0.;
 #pragma unroll
                                 for (int n = 0; n < NC; ++n) {
@@ -539,16 +539,16 @@ rys_jk_warp_kernel(JKTask t)
                                 double dqs[NFS], dps[NFS], kps[NFS], kqs[NFS];
 #pragma unroll
                                 for (int d = 0; d < NFS; ++d) {
-                                    dqs[d] = dm[qrow + s0 + d];
-                                    dps[d] = dm[prow + s0 + d];
+                                    dqs[d] = __ldg(dm + qrow + s0 + d);
+                                    dps[d] = __ldg(dm + prow + s0 + d);
                                     kps[d] = 0.;
                                     kqs[d] = 0.;
                                 }
 #pragma unroll
                                 for (int n = 0; n < NC; ++n) {
                                     if (c0 + n < NFR) {
-                                        double dqr = dm[qrow + r0 + c0 + n];
-                                        double dpr = dm[prow + r0 + c0 + n];
+                                        double dqr = __ldg(dm + qrow + r0 + c0 + n);
+                                        double dpr = __ldg(dm + prow + r0 + c0 + n);
                                         double kpr = 0., kqr = 0.;
 #pragma unroll
                                         for (int d = 0; d < NFS; ++d) {

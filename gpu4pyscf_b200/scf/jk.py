@@ -103,6 +103,8 @@ class _VHFOpt:
         self.sorted_mol = None
         self.bas_pair_cache = None
         self._rys_envs = None
+        self._tasks = None
+        self._qmax_cache = None
         return self
 
     # ------------------------------------------------------------------
@@ -157,24 +159,28 @@ class _VHFOpt:
     # ------------------------------------------------------------------
     def class_tasks(self):
         '''Launch list: (group pair Y, group pair X, dedupe) for every unordered
-        pair of group pairs; X is the pair type with more Cartesian components.'''
+        pair of group pairs.  Y is the lane side and X the register-tile side of
+        the kernel; the library says which orientation of a class it instantiates.'''
+        if getattr(self, '_tasks', None) is not None:
+            return self._tasks
+        lib = loader.load_library()
         smol = self.sorted_mol
         uniq = smol.uniq_l_ctr
         keys = sorted(self.bas_pair_cache.keys())
 
-        def nf2(key):
-            li, lj = int(uniq[key[0], 0]), int(uniq[key[1], 0])
-            return ((li + 1) * (li + 2) // 2) * ((lj + 1) * (lj + 2) // 2), (li, lj)
+        def ls(key):
+            return int(uniq[key[0], 0]), int(uniq[key[1], 0])
 
         tasks = []
         for ia, ka in enumerate(keys):
             for kb in keys[:ia + 1]:
                 if ka == kb:
                     tasks.append((ka, ka, 1))
-                elif nf2(ka) >= nf2(kb):
+                elif lib.B200_has_class(*ls(kb), *ls(ka)):
                     tasks.append((kb, ka, 0))      # (Y, X)
                 else:
                     tasks.append((ka, kb, 0))
+        self._tasks = tasks
         return tasks
 
     def get_jk(self, dms, hermi=0, verbose=None, with_j=True, with_k=True):

@@ -80,6 +80,12 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream);
 
+/* 1 if a kernel is instantiated with (lp,lq) as the lane side (Y) and (lr,ls)
+ * as the register-tile side (X); exactly one orientation of every unordered
+ * angular class exists.  Plays the role of the reference's kernel-selection
+ * switch (rys_contract_jk.cu:395-440). */
+int B200_has_class(int lp, int lq, int lr, int ls);
+
 /* Schwarz bounds q = 1/2 log max|(ij|ij)| for a list of shell pairs of one
  * (li, lj, nprim_i, nprim_j) class.  Replaces int2e_qcond_estimator,
  * lib/gvhf-rys/nr_sr_estimator.cu:416-430 (called from scf/jk.py:1076-1086). */

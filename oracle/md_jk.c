@@ -358,6 +358,24 @@ void oracle_q_cond(double *q, const int *atm, int natm, const int *bas, int nbas
  * screen != 0: skip shell quartets with q_ij*q_kl*max|D| < tol (libcvhf direct-SCF
  * prescreening, CVHFnrs8_prescreen restated); returns number of quartets computed.
  */
+/* Algorithmic flop model of SURVEY.md section 8d (same formula as
+ * gpu4pyscf_b200/scf/flops.py) accumulated over the quartets oracle_jk computes,
+ * so that a CPU timing on a fragment can be scaled to the full workload. */
+static double g_last_flops = 0.;
+double oracle_last_flops(void) { return g_last_flops; }
+static int nf_l(int l) { return (l + 1) * (l + 2) / 2; }
+static double falg_quartet(int li, int lj, int lk, int ll, double nprim, int n_dm)
+{
+    int lij = li + lj, lkl = lk + ll;
+    int nroots = (lij + lkl) / 2 + 1;
+    double nfq = (double)nf_l(li) * nf_l(lj) * nf_l(lk) * nf_l(ll);
+    double f2d = 4. * lij + 6. * (lij + 1) * lkl;
+    for (int j = 0; j < lj; j++) f2d += 2. * (lkl + 1) * (lij - j);
+    for (int l = 0; l < ll; l++) f2d += 2. * (li + 1) * (lj + 1) * (lkl - l);
+    double fprim = 40. + 76. * nroots + nroots * (24. + 3. * f2d + 3. * nfq);
+    return nprim * fprim + 12. * nfq * n_dm;
+}
+
 long oracle_jk(double *vj, double *vk, const double *dm, int n_dm, int nao,
                const int *atm, int natm, const int *bas, int nbas, const double *env,
                double omega, int screen, double tol, int with_j, int with_k)
@@ -387,8 +405,9 @@ long oracle_jk(double *vj, double *vk, const double *dm, int n_dm, int nao,
     memset(vj, 0, sizeof(double) * nao2 * n_dm);
     memset(vk, 0, sizeof(double) * nao2 * n_dm);
     long ncomputed = 0;
+    double flops = 0.;
     int npair = nbas * (nbas + 1) / 2;
-#pragma omp parallel reduction(+:ncomputed)
+#pragma omp parallel reduction(+:ncomputed,flops)
     {
         double *tj = (double *)calloc(nao2 * n_dm, sizeof(double));
         double *tk = (double *)calloc(nao2 * n_dm, sizeof(double));
@@ -424,6 +443,12 @@ long oracle_jk(double *vj, double *vk, const double *dm, int n_dm, int nao,
                 if (n > cap) { free(buf); buf = (double *)malloc(sizeof(double) * n); cap = n; }
                 eri_block(buf, si, sj, sk, sl, omega);
                 ncomputed++;
+                {   /* class in the kernels' canonical order: higher l first within a pair */
+                    int a = bas[i*8+1], b = bas[j*8+1], c = bas[k*8+1], d = bas[l*8+1];
+                    double np = (double)bas[i*8+2] * bas[j*8+2] * bas[k*8+2] * bas[l*8+2]
+                              * bas[i*8+3] * bas[j*8+3] * bas[k*8+3] * bas[l*8+3];
+                    flops += falg_quartet(a > b ? a : b, a > b ? b : a, c > d ? c : d, c > d ? d : c, np, n_dm);
+                }
                 /* the (up to) 8 distinct index permutations of this quartet */
                 int perm[8][4] = {{0,1,2,3},{1,0,2,3},{0,1,3,2},{1,0,3,2},
                                   {2,3,0,1},{3,2,0,1},{2,3,1,0},{3,2,1,0}};
@@ -464,6 +489,7 @@ long oracle_jk(double *vj, double *vk, const double *dm, int n_dm, int nao,
         free(tj); free(tk); free(buf);
     }
     free(ao_loc); free(q); free(dmax);
+    g_last_flops = flops;
     return ncomputed;
 }
 

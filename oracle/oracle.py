@@ -26,6 +26,7 @@ def _lib():
     if _LIB is None:
         _LIB = ctypes.CDLL(build())
         _LIB.oracle_jk.restype = ctypes.c_long
+        _LIB.oracle_last_flops.restype = ctypes.c_double
     return _LIB
 
 
@@ -85,6 +86,11 @@ def get_jk(mol, dm, hermi=0, omega=None, screen=False, tol=1e-13,
     if return_count:
         return vj, vk, n
     return vj, vk
+
+
+def last_flops():
+    """Algorithmic flops (SURVEY.md 8d model) of the quartets the last get_jk call evaluated."""
+    return float(_lib().oracle_last_flops())
 
 
 def q_cond(mol, omega=0.):
