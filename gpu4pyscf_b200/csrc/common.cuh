@@ -68,6 +68,8 @@ struct JKTask {
     unsigned long long *counter;  // optional: number of quartets evaluated (measurement)
     int nq;                 // quartet slots per block
     int slot_doubles;       // shared-memory doubles per slot
+    int ychunk;             // work item = (X pair, chunk of `ychunk` consecutive Y candidates)
+    int nychunk;            // ceil(npair_y / ychunk)
 };
 
 // ---- Cartesian component tables (lexical order xx, xy, xz, yy, yz, zz ...;

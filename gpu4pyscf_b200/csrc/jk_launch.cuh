@@ -1,6 +1,7 @@
 // Launch-shape selection for one class instantiation (plays the role of the
 // reference's threads_scheme_for_k, gpu4pyscf/lib/gvhf-rys/rys_contract_k.cu:542-597).
 #pragma once
+#include <stdlib.h>
 #include "rt.h"
 #include "rys_jk_kernel.cuh"
 #include "rys_jk_thread.cuh"
@@ -8,6 +9,21 @@
 
 
 typedef int (*jk_launcher_t)(JKTask *t, int nsm, int smem_max, cudaStream_t stream);
+
+// Split the Y lists into chunks so that there are enough (X pair, Y chunk) work
+// items for `workers` independent warps/teams; returns the number of items of
+// this rank.
+static inline int jk_set_chunks(JKTask *t, int workers)
+{
+    int ch = 1024;
+    static const char *force = getenv("B200_YCHUNK");     // tests: exercise the chunk logic on tiny inputs
+    if (force != nullptr && atoi(force) > 0) ch = atoi(force);
+    else while (ch > 128 && (long long)t->npair_x * ((t->npair_y + ch - 1) / ch) < 8LL * workers * t->world) ch >>= 1;
+    t->ychunk = ch;
+    t->nychunk = (t->npair_y + ch - 1) / ch;
+    long long items = (long long)t->npair_x * t->nychunk;
+    return (int)((items + t->world - 1) / t->world);
+}
 
 template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
 int jk_launch(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
@@ -31,6 +47,8 @@ int jk_launch(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     }
     t->nq = nq;
     t->slot_doubles = slot;
+    t->ychunk = t->npair_y;
+    t->nychunk = 1;
     int nt = nq * C::G;
     int per_sm = rt_prepare(rys_jk_kernel<LP, LQ, LR, LS, NCS, NDM>, smem, nt);
     if (per_sm < 1) {
@@ -58,7 +76,7 @@ int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         return 1;
     }
     int nt = JKT_THREADS;
-    int smem = (RysSmem<C::NROOTS>::DOUBLES + jk_blk_doubles(NDM, C::NFRS, nt, nt)) * 8;
+    int smem = (RysSmem<C::NROOTS>::DOUBLES + (nt / 32) * jkt_warp_doubles(nrs, NDM, C::NFRS)) * 8;
     t->nq = nt;
     t->slot_doubles = 0;
     int per_sm = rt_prepare(rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>, smem, nt);
@@ -66,9 +84,9 @@ int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         fprintf(stderr, "rys_jk_thread: class (%d%d|%d%d) cannot be made resident\n", LP, LQ, LR, LS);
         return 1;
     }
-    int nitems = (t->npair_x + t->world - 1) / t->world;
     int grid = nsm * per_sm;
-    if (grid > nitems) grid = nitems;
+    int nitems = jk_set_chunks(t, grid * (nt / 32));
+    if (grid * (nt / 32) > nitems) grid = (nitems + nt / 32 - 1) / (nt / 32);
     if (grid < 1) return 0;
     KLAUNCH((rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_thread_kernel");
@@ -89,8 +107,9 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     const int nteams = JKW_MAXTHREADS / C::TEAM;
     const int nt = nteams * C::TEAM;
     const int nprimq = npq * nrs;
-    // g-sets per lane slot: enough to occupy a warp in the root phase
-    int K = (32 + C::NSW * 2 * C::NROOTS - 1) / (C::NSW * 2 * C::NROOTS);
+    // g-sets per lane slot: fill (not overfill) the team in the recurrence phase,
+    // whose work items are (g-set, root, axis)
+    int K = C::TEAM / (C::NSW * 3 * C::NROOTS);
     if (K > 4) K = 4;
     if (K < 1) K = 1;
     if (nprimq > 1 && K > nprimq) K = nprimq;
@@ -114,8 +133,8 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
                 LP, LQ, LR, LS, smem, nt);
         return 1;
     }
-    int nitems = (t->npair_x + t->world - 1) / t->world;
     int grid = nsm * per_sm;
+    int nitems = jk_set_chunks(t, grid * nteams);
     if (grid * nteams > nitems) grid = (nitems + nteams - 1) / nteams;
     if (grid < 1) return 0;
     KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM>), grid, nt, smem, stream, *t);

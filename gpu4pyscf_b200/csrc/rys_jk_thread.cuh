@@ -22,11 +22,15 @@ __host__ __device__ constexpr int jkt_minblocks(int nf_total)
 // block-wide sum of per-thread values through shuffles + one smem stage
 __device__ __forceinline__ double jkt_warp_sum(double v)
 {
-#ifndef CPU_EMUL
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-#endif
     return v;
+}
+
+// shared-memory doubles of one warp: ints, X primitive pairs, D_rs block, 64-entry queue
+__host__ __device__ inline int jkt_warp_doubles(int nrs, int ndm, int nfrs)
+{
+    return (2 + nrs * 5 + ndm * nfrs + 32 + 1) & ~1;
 }
 
 template <int LP, int LQ, int LR, int LS, int NDM>
@@ -54,34 +58,41 @@ rys_jk_thread_kernel(JKTask t)
     const bool do_j = t.vj != nullptr;
     const bool do_k = t.vk != nullptr;
 
+    // every warp is an independent worker: own X pair, own survivor queue
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
     double *rys_tab = smem;                          // Rys tables of this NROOTS (rys_roots.cuh)
-    double *blk = smem + RysSmem<NROOTS>::DOUBLES;
-    int *blk_ints = (int *)(blk + BLK_INTS);
-    double *drs = blk + BLK_DRS;
-    uint32_t *queue = (uint32_t *)(blk + BLK_DRS + NDM * NFRS);
+    double *wsm = smem + RysSmem<NROOTS>::DOUBLES + warp * jkt_warp_doubles(nrs, NDM, NFRS);
+    int *w_ints = (int *)wsm;                        // [0] ix
+    double *rsprim = wsm + 2;                        // nrs * 5: eta, Qx, Qy, Qz, coef
+    double *drs = rsprim + nrs * 5;
+    uint32_t *queue = (uint32_t *)(drs + NDM * NFRS);  // 64 entries
     rys_stage_tables<NROOTS>(rys_tab, t.rys_cheb, t.rys_large, tid, NT);
+    __syncthreads();
 
     const int *bas = t.bas;
     const double *env = t.env;
     const int *ao_loc = t.ao_loc;
 
     while (true) {
-        __syncthreads();
-        if (tid == 0) {
-            blk_ints[0] = atomicAdd(t.head, 1) * t.world + t.rank;
-            blk_ints[1] = 0;
-            blk_ints[2] = 0;
-        }
-        __syncthreads();
-        const int ix = blk_ints[0];
-        if (ix >= t.npair_x) break;
+        __syncwarp();
+        if (lane == 0) w_ints[0] = atomicAdd(t.head, 1) * t.world + t.rank;
+        __syncwarp();
+        // work item = (X pair ix, chunk of the q-sorted Y list), chunk-major
+        const int item = w_ints[0];
+        if (item >= t.npair_x * t.nychunk) break;
+        const int chunk = item / t.npair_x;
+        const int ix = item - chunk * t.npair_x;
+        const float thr = t.cutoff - t.q_x[ix];
+        int ypos = chunk * t.ychunk;
+        if (t.dedupe == 1 && ypos < ix) ypos = ix;
+        const int y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
+        if (ypos >= y_end || t.q_y[ypos] + t.dm_penalty + t.q_margin < thr) continue;   // dead chunk
         const uint32_t pair_rs = t.pair_x[ix];
         const int rsh = pair_rs / nbas;
         const int ssh = pair_rs - rsh * nbas;
         const int r0 = ao_loc[rsh];
         const int s0 = ao_loc[ssh];
-        const float qx = t.q_x[ix];
-        const float thr = t.cutoff - qx;
         const double *Rr = env + bas[rsh * BAS_SLOTS + PTR_BAS_COORD];
         const double *Rs = env + bas[ssh * BAS_SLOTS + PTR_BAS_COORD];
         const double Cx = Rr[0], Cy = Rr[1], Cz = Rr[2];
@@ -92,20 +103,20 @@ rys_jk_thread_kernel(JKTask t)
             const double *cr = env + bas[rsh * BAS_SLOTS + PTR_COEFF];
             const double *cs = env + bas[ssh * BAS_SLOTS + PTR_COEFF];
             double rr2 = CDx * CDx + CDy * CDy + CDz * CDz;
-            for (int i = tid; i < nrs; i += NT) {
+            for (int i = lane; i < nrs; i += 32) {
                 int ir = i / t.nprim_s;
                 int is = i - ir * t.nprim_s;
                 double ar = er[ir], as = es[is];
                 double eta = ar + as;
                 double f = as / eta;
-                double *o = blk + BLK_RSPRIM + i * 5;
+                double *o = rsprim + i * 5;
                 o[0] = eta;
                 o[1] = Cx - f * CDx;
                 o[2] = Cy - f * CDy;
                 o[3] = Cz - f * CDz;
                 o[4] = cr[ir] * cs[is] * exp(-ar * f * rr2);
             }
-            for (int i = tid; i < NDM * NFRS; i += NT) {
+            for (int i = lane; i < NDM * NFRS; i += 32) {
                 int idm = i / NFRS;
                 int cd = i - idm * NFRS;
                 int c = cd / NFS;
@@ -119,27 +130,24 @@ rys_jk_thread_kernel(JKTask t)
 #pragma unroll
             for (int n = 0; n < NFRS; ++n) jacc[idm][n] = 0.;
 
-        int ypos = (t.dedupe == 1) ? ix : 0;
         const float *dc_r = t.dm_cond + (size_t)rsh * nbas;
         const float *dc_s = t.dm_cond + (size_t)ssh * nbas;
         const float d_rs = dc_r[ssh];
-        __syncthreads();
+        int qn = 0;
+        bool exhausted = false;
+        __syncwarp();
 
         while (true) {
-            // ---------------- fill the queue ----------------
-            while (true) {
-                int qn = blk_ints[1];
-                int exhausted = blk_ints[2];
-                __syncthreads();
-                if (exhausted || qn >= NT) break;
-                int y = ypos + tid;
-                bool keep = false;
-                if (y >= t.npair_y) {
-                    blk_ints[2] = 1;
+            // ---------------- screen Y pairs into the warp's queue (ballot compaction) ----------------
+            while (!exhausted && qn < 32) {
+                const int y = ypos + lane;
+                bool keep = false, stop = false;
+                if (y >= y_end) {
+                    stop = true;
                 } else {
                     float qy = t.q_y[y];
                     if (qy + t.dm_penalty + t.q_margin < thr) {
-                        blk_ints[2] = 1;
+                        stop = true;                  // sorted: nothing further survives
                     } else {
                         uint32_t pair_pq = t.pair_y[y];
                         int psh = pair_pq / nbas;
@@ -159,21 +167,18 @@ rys_jk_thread_kernel(JKTask t)
                         }
                     }
                 }
-                if (keep) {
-                    int pos = atomicAdd(&blk_ints[1], 1);
-                    queue[pos] = (uint32_t)y;
-                }
-                ypos += NT;
-                __syncthreads();
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint32_t)y;
+                qn += __popc(m);
+                exhausted = __any_sync(0xffffffffu, stop);
+                ypos += 32;
+                __syncwarp();
             }
-            const int qn = blk_ints[1];
-            const int exhausted = blk_ints[2];
-            const int nsteps = exhausted ? (qn + NT - 1) / NT : qn / NT;
+            if (qn == 0) break;
+            const int nb = qn < 32 ? qn : 32;
 
-            for (int step = 0; step < nsteps; ++step) {
-                const int qi = step * NT + tid;
-                if (qi >= qn) continue;
-                const int iy = queue[qi];
+            if (lane < nb) {
+                const int iy = queue[lane];
                 const uint32_t pair_pq = t.pair_y[iy];
                 const int psh = pair_pq / nbas;
                 const int qsh = pair_pq - psh * nbas;
@@ -205,7 +210,7 @@ rys_jk_thread_kernel(JKTask t)
                     const double Px = Ax - fq * ABx, Py = Ay - fq * ABy, Pz = Az - fq * ABz;
                     const double cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
                     for (int irs = 0; irs < nrs; ++irs) {
-                        const double *rr = blk + BLK_RSPRIM + irs * 5;
+                        const double *rr = rsprim + irs * 5;
                         const double eta = rr[0];
                         const double PQx = Px - rr[1], PQy = Py - rr[2], PQz = Pz - rr[3];
                         const double ze = zeta + eta;
@@ -392,20 +397,19 @@ rys_jk_thread_kernel(JKTask t)
                         }
                     }
                 }
-            }   // steps
+            }   // lane < nb
 
-            __syncthreads();
-            const int rem = qn - nsteps * NT;
-            if (tid == 0 && t.counter != nullptr) {
-                atomicAdd(t.counter, (unsigned long long)(rem > 0 ? nsteps * NT : qn));
-            }
+            // ---------------- keep the unprocessed remainder of the queue ----------------
+            __syncwarp();
+            if (lane == 0 && t.counter != nullptr) atomicAdd(t.counter, (unsigned long long)nb);
+            const int rem = qn - nb;
             uint32_t keepv = 0;
-            if (rem > 0 && tid < rem) keepv = queue[nsteps * NT + tid];
-            __syncthreads();
-            if (rem > 0 && tid < rem) queue[tid] = keepv;
-            if (tid == 0) blk_ints[1] = rem > 0 ? rem : 0;
-            __syncthreads();
-            if (exhausted) break;
+            if (lane < rem) keepv = queue[nb + lane];
+            __syncwarp();
+            if (lane < rem) queue[lane] = keepv;
+            qn = rem;
+            __syncwarp();
+            if (exhausted && qn == 0) break;
         }
 
         // ---------------- flush J_rs: warp reduction, one atomic per warp ----------------
@@ -416,10 +420,7 @@ rys_jk_thread_kernel(JKTask t)
 #pragma unroll
                 for (int cd = 0; cd < NFRS; ++cd) {
                     double v = jkt_warp_sum(jacc[idm][cd]);
-#ifndef CPU_EMUL
-                    if ((tid & 31) == 0)
-#endif
-                    if (v != 0.) JK_ATOMIC_ADD(vj + (size_t)(r0 + cd / NFS) * nao + s0 + cd % NFS, v);
+                    if (lane == 0 && v != 0.) JK_ATOMIC_ADD(vj + (size_t)(r0 + cd / NFS) * nao + s0 + cd % NFS, v);
                 }
             }
         }

@@ -33,7 +33,10 @@ struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
     static constexpr int TW = (B::G + 31) / 32;          // warps per team
     static constexpr int TEAM = TW * 32;
     static constexpr int NSW = TW == 1 ? 32 / B::G : 1;  // quartets per team in the contraction phase
-    static constexpr int GSET = (2 * B::NROOTS + 3 * B::NROOTS * (B::G2SIZE + B::GSIZE)) | 1;
+    // odd strides: lanes writing/reading consecutive (ea,eb) segments hit distinct banks
+    static constexpr int SUBP = B::SUBSIZE | 1;
+    static constexpr int GSIZEP = ((LP + 1) * (LQ + 1) * SUBP) | 1;
+    static constexpr int GSET = (2 * B::NROOTS + 3 * B::NROOTS * GSIZEP) | 1;
     // registers: gout + J_rs accumulators + one root's gx/gy/gz tile
     static constexpr int TILE = B::NC * B::NFS;
 };
@@ -69,12 +72,12 @@ __device__ __forceinline__ void jkw_team_sync(int team)
 // resident blocks per SM asked from the register allocator, by register-tile size
 __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int team)
 {
-    // doubles live in the contraction phase: gout + jacc*ndm + 3*sub
-    int d = tile * (1 + ndm) + 3 * sub;
-    int regs = 2 * d + 48;
+    // doubles that stay live across the whole Y stream: gout + J_rs accumulators
+    int d = tile * (1 + ndm);
     int threads = (JKW_MAXTHREADS / team) * team;
-    int nb = 65536 / (regs * threads);
-    return nb < 1 ? 1 : (nb > 4 ? 4 : nb);
+    int nb = d <= 24 ? 3 : (d <= 44 ? 2 : 1);      // 256 threads: 85 / 128 / 255 registers
+    (void)sub;
+    return threads <= 128 ? 2 * nb : nb;
 }
 
 template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
@@ -88,10 +91,9 @@ rys_jk_warp_kernel(JKTask t)
     typedef JKWCfg<LP, LQ, LR, LS, NCS> C;
     constexpr int NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS, NFRS = C::NFRS;
     constexpr int LPQ = C::LPQ, LRS = C::LRS, NROOTS = C::NROOTS;
-    constexpr int G2SIZE = C::G2SIZE, GSIZE = C::GSIZE, NC = C::NC, G = C::G;
-    constexpr int SUB = C::SUBSIZE;
+    constexpr int NC = C::NC, G = C::G;
+    constexpr int SUB = C::SUBSIZE, SUBP = C::SUBP, GSIZEP = C::GSIZEP;
     constexpr int TW = C::TW, TEAM = C::TEAM, NSW = C::NSW, GSET = C::GSET;
-    constexpr int NAB2 = (LP + 1) * (LQ + 1);
 
 #ifdef CPU_EMUL
     double *smem = (double *)emul_dynamic_smem;
@@ -145,9 +147,9 @@ rys_jk_warp_kernel(JKTask t)
     const int a = ab / NFQ;
     const int b = ab - a * NFQ;
     const int c0 = cpart * NC;
-    const int gbx = (cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * SUB;
-    const int gby = (cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * SUB + GSIZE;
-    const int gbz = (cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * SUB + 2 * GSIZE;
+    const int gbx = (cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * SUBP;
+    const int gby = (cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * SUBP + GSIZEP;
+    const int gbz = (cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * SUBP + 2 * GSIZEP;
     int ox[NC], oy[NC], oz[NC];
 #pragma unroll
     for (int n = 0; n < NC; ++n) {
@@ -167,14 +169,22 @@ rys_jk_warp_kernel(JKTask t)
             tm_ints[2] = 0;
         }
         jkw_team_sync<TW>(team);
-        const int ix = tm_ints[0];
-        if (ix >= t.npair_x) break;
+        // work item = (X pair ix, chunk of the q-sorted Y list); chunk-major order
+        // so that the dense leading chunks of every X pair are handed out first
+        const int item = tm_ints[0];
+        if (item >= t.npair_x * t.nychunk) break;
+        const int chunk = item / t.npair_x;
+        const int ix = item - chunk * t.npair_x;
+        const float thr = t.cutoff - t.q_x[ix];
+        int ypos = chunk * t.ychunk;
+        if (t.dedupe == 1 && ypos < ix) ypos = ix;
+        const int y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
+        if (ypos >= y_end || t.q_y[ypos] + t.dm_penalty + t.q_margin < thr) continue;   // dead chunk
         const uint32_t pair_rs = t.pair_x[ix];
         const int rsh = pair_rs / nbas;
         const int ssh = pair_rs - rsh * nbas;
         const int r0 = ao_loc[rsh];
         const int s0 = ao_loc[ssh];
-        const float thr = t.cutoff - t.q_x[ix];
         {
             const double *Rr = env + bas[rsh * BAS_SLOTS + PTR_BAS_COORD];
             const double *Rs = env + bas[ssh * BAS_SLOTS + PTR_BAS_COORD];
@@ -217,7 +227,6 @@ rys_jk_warp_kernel(JKTask t)
 #pragma unroll
                 for (int d = 0; d < NFS; ++d) jacc[idm][n][d] = 0.;
 
-        int ypos = (t.dedupe == 1) ? ix : 0;
         const float *dc_r = t.dm_cond + (size_t)rsh * nbas;
         const float *dc_s = t.dm_cond + (size_t)ssh * nbas;
         const float d_rs = dc_r[ssh];
@@ -230,7 +239,7 @@ rys_jk_warp_kernel(JKTask t)
             while (!exhausted && qn < nqs) {
                 const int y = ypos + lt;
                 bool keep = false, stop = false;
-                if (y >= t.npair_y) {
+                if (y >= y_end) {
                     stop = true;
                 } else {
                     float qy = t.q_y[y];
@@ -361,7 +370,7 @@ rys_jk_warp_kernel(JKTask t)
                     }
                 }
                 jkw_team_sync<TW>(team);
-                // ---------------- phase 2: VRR + TRR, one (g-set, root, axis) per lane ----------------
+                // ---------------- phase 2: VRR + TRR + HRR, one (g-set, root, axis) per lane ----------------
                 for (int it = lt; it < ngs * 3 * NROOTS; it += TEAM) {
                     const int g = it / (3 * NROOTS);
                     const int ra = it - g * (3 * NROOTS);
@@ -412,62 +421,47 @@ rys_jk_warp_kernel(JKTask t)
                                 gg[f + 1][e] = cpq * gg[f][e] + f * b01 * gg[f - 1][e] + e * b00 * gg[f][e - 1];
                         }
                     }
-                    double *o = gs + 2 * NROOTS + ra * G2SIZE;
-#pragma unroll
-                    for (int f = 0; f <= LRS; ++f)
-#pragma unroll
-                        for (int e = 0; e <= LPQ; ++e) o[f * (LPQ + 1) + e] = gg[f][e];
-                }
-                jkw_team_sync<TW>(team);
-                // ---------------- phase 3: HRR (bra then ket), one (g-set, root, axis, ea, eb) per lane ----------------
-                for (int it = lt; it < ngs * 3 * NROOTS * NAB2; it += TEAM) {
-                    const int g = it / (3 * NROOTS * NAB2);
-                    const int r3 = it - g * (3 * NROOTS * NAB2);
-                    const int ra = r3 / NAB2;
-                    const int ab2 = r3 - ra * NAB2;
-                    const int ea = ab2 / (LQ + 1);
-                    const int eb = ab2 - ea * (LQ + 1);
-                    const int axis = ra % 3;
-                    const int j = single ? g : g % NSW;
-                    const double AB = slots[j * slot_d + axis];
+                    // HRR on the registers (bra, then ket), result to shared memory:
+                    // g[ra][(ea, eb)][c * (LS+1) + d], (ea, eb) segments SUBP apart
+                    const double AB = sl[axis];
                     const double CD = rsgeom[axis];
-                    double *gs = gsets + g * GSET;
-                    const double *in = gs + 2 * NROOTS + ra * G2SIZE + ea;
-                    double v[LRS + 1];
+                    double *o = gs + 2 * NROOTS + ra * GSIZEP;
 #pragma unroll
-                    for (int f = 0; f <= LRS; ++f) {
-                        double u[LQ + 1];
+                    for (int eb = 0; eb <= LQ; ++eb) {
+                        // gg[f][ea] now holds the bra-transferred value for (ea, eb)
 #pragma unroll
-                        for (int e = 0; e <= LQ; ++e) u[e] = (e <= eb) ? in[f * (LPQ + 1) + e] : 0.;
+                        for (int ea = 0; ea <= LP; ++ea) {
+                            double v[LRS + 1];
 #pragma unroll
-                        for (int k = 0; k < LQ; ++k) {
-                            if (k < eb) {
+                            for (int f = 0; f <= LRS; ++f) v[f] = gg[f][ea];
 #pragma unroll
-                                for (int e = 0; e < LQ - k; ++e) u[e] = u[e + 1] + AB * u[e];
+                            for (int d = 0; d <= LS; ++d) {
+#pragma unroll
+                                for (int c = 0; c <= LR; ++c)
+                                    o[(ea * (LQ + 1) + eb) * SUBP + c * (LS + 1) + d] = v[c];
+                                if (d < LS) {
+#pragma unroll
+                                    for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                                }
                             }
                         }
-                        v[f] = u[0];
-                    }
-                    double *o = gs + 2 * NROOTS + 3 * NROOTS * G2SIZE + ra * GSIZE + ab2 * SUB;
+                        if (eb < LQ) {
 #pragma unroll
-                    for (int d = 0; d <= LS; ++d) {
+                            for (int f = 0; f <= LRS; ++f)
 #pragma unroll
-                        for (int c = 0; c <= LR; ++c) o[c * (LS + 1) + d] = v[c];
-                        if (d < LS) {
-#pragma unroll
-                            for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                                for (int e = 0; e < LPQ - eb; ++e) gg[f][e] = gg[f][e + 1] + AB * gg[f][e];
                         }
                     }
                 }
                 jkw_team_sync<TW>(team);
                 // ---------------- phase 4: gout += gx * gy * gz ; digestion ----------------
                 for (int k = 0; k < K; ++k) {
-                    const double *gk = gsets + (k * NSW + s4) * GSET + 2 * NROOTS + 3 * NROOTS * G2SIZE;
+                    const double *gk = gsets + (k * NSW + s4) * GSET + 2 * NROOTS;
                     if (lane_on) {
                         if (NCS == 1) {
 #pragma unroll
                             for (int root = 0; root < NROOTS; ++root) {
-                                const double *gr = gk + root * 3 * GSIZE;
+                                const double *gr = gk + root * 3 * GSIZEP;
                                 double gx[SUB], gy[SUB], gz[SUB];
 #pragma unroll
                                 for (int i = 0; i < SUB; ++i) {
@@ -487,7 +481,7 @@ rys_jk_warp_kernel(JKTask t)
                             }
                         } else {
                             for (int root = 0; root < NROOTS; ++root) {
-                                const double *gr = gk + root * 3 * GSIZE;
+                                const double *gr = gk + root * 3 * GSIZEP;
 #pragma unroll
                                 for (int n = 0; n < NC; ++n) {
                                     double gx[LS + 1], gy[LS + 1], gz[LS + 1];

@@ -87,6 +87,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
 }
 static inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int min(int a, int b) { return a < b ? a : b; }
 static inline double atomicAdd(double *p, double v) { double o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }

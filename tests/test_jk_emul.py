@@ -22,6 +22,8 @@ from tests import molecules
 case, hermi = sys.argv[1], int(sys.argv[2])
 if case == 'sto':
     mol = molecules.water('sto-3g')
+elif case == 'tz':
+    mol = molecules.water('def2-tzvp')      # contracted p shells: multi-pass primitive batches
 else:
     mol = molecules.mol1_lmax(int(case))
 np.random.seed(1)
@@ -40,8 +42,11 @@ print('OK')
 ''' % ROOT
 
 
-@pytest.mark.parametrize('case,hermi', [('sto', 1), ('sto', 0), ('sto', 2), ('2', 1), ('3', 0)])
-def test_emulated_kernels_match_oracle(case, hermi):
-    r = subprocess.run([sys.executable, '-c', SCRIPT, case, str(hermi)],
+@pytest.mark.parametrize('case,hermi,ychunk', [('sto', 1, 0), ('sto', 0, 3), ('sto', 2, 0), ('2', 1, 7), ('3', 0, 0), ('tz', 1, 5)])
+def test_emulated_kernels_match_oracle(case, hermi, ychunk):
+    env = dict(os.environ)
+    if ychunk:
+        env['B200_YCHUNK'] = str(ychunk)      # tiny Y chunks: many (X pair, Y chunk) work items
+    r = subprocess.run([sys.executable, '-c', SCRIPT, case, str(hermi)], env=env,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and 'OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
