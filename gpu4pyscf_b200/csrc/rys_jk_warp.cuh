@@ -33,10 +33,17 @@ struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
     static constexpr int TW = (B::G + 31) / 32;          // warps per team
     static constexpr int TEAM = TW * 32;
     static constexpr int NSW = TW == 1 ? 32 / B::G : 1;  // quartets per team in the contraction phase
-    // odd strides: lanes writing/reading consecutive (ea,eb) segments hit distinct banks
-    static constexpr int SUBP = B::SUBSIZE | 1;
-    static constexpr int GSIZEP = ((LP + 1) * (LQ + 1) * SUBP) | 1;
-    static constexpr int GSET = (2 * B::NROOTS + 3 * B::NROOTS * GSIZEP) | 1;
+    // strides (in doubles) are even with an odd half: segments are 16-byte aligned
+    // for 128-bit shared-memory accesses and consecutive segments / (root,axis)
+    // blocks / g-sets start in different 16-byte bank groups
+    static constexpr int oddhalf(int n) { return (n + (n & 1)) + ((((n + (n & 1)) / 2) % 2 == 0) ? 2 : 0); }
+    // NCS == 1: a segment holds the bra-transferred g(ea,eb; f), f = 0..LR+LS, and the
+    // ket transfer runs in registers in the contraction phase (fewer shared-memory
+    // bytes per FMA); NCS > 1: a segment holds the final (c,d) block
+    static constexpr int SEG = NCS == 1 ? B::LRS + 1 : B::SUBSIZE;
+    static constexpr int SUBP = oddhalf(SEG);
+    static constexpr int GSIZEP = oddhalf((LP + 1) * (LQ + 1) * SUBP);
+    static constexpr int GSET = oddhalf(2 * B::NROOTS + 3 * B::NROOTS * GSIZEP);
     // registers: gout + J_rs accumulators + one root's gx/gy/gz tile
     static constexpr int TILE = B::NC * B::NFS;
 };
@@ -50,8 +57,9 @@ __host__ __device__ inline int jkw_team_doubles(int team_threads, int nsw, int K
     int ngs = nsw * K;
     int nqs = (npq * nrs == 1) ? ngs : nsw;
     int qcap = nqs + team_threads;
-    int n = 8 + nrs * 5 + ndm * nfrs + (qcap + 1) / 2 + nqs * (JKW_SLOT_HDR + 5 * npq) + ngs * gset;
-    return (n + 1) & ~1;
+    int n = 8 + nrs * 5 + ndm * nfrs + (qcap + 1) / 2 + nqs * (JKW_SLOT_HDR + 5 * npq);
+    n = (n + 1) & ~1;                    // g-sets start 16-byte aligned
+    return n + ngs * gset;
 }
 
 template <int TW>
@@ -64,6 +72,31 @@ __device__ __forceinline__ void jkw_team_sync(int team)
     if (TW == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "r"(TW * 32) : "memory");
 #endif
+}
+
+// 16-byte shared-memory vector access of an N-double segment (p is 16-byte aligned)
+template <int N>
+__device__ __forceinline__ void jkw_ld_seg(double (&dst)[N], const double *p)
+{
+#pragma unroll
+    for (int i = 0; i + 1 < N; i += 2) {
+        double2 v = *(const double2 *)(p + i);
+        dst[i] = v.x;
+        dst[i + 1] = v.y;
+    }
+    if (N & 1) dst[N - 1] = p[N - 1];
+}
+template <int N>
+__device__ __forceinline__ void jkw_st_seg(double *p, const double (&src)[N])
+{
+#pragma unroll
+    for (int i = 0; i + 1 < N; i += 2) {
+        double2 v;
+        v.x = src[i];
+        v.y = src[i + 1];
+        *(double2 *)(p + i) = v;
+    }
+    if (N & 1) p[N - 1] = src[N - 1];
 }
 
 #ifndef JKW_MAXTHREADS
@@ -127,7 +160,7 @@ rys_jk_warp_kernel(JKTask t)
     double *drs = rsprim + nrs * 5;
     uint32_t *queue = (uint32_t *)(drs + NDM * NFRS);
     double *slots = drs + NDM * NFRS + (qcap + 1) / 2;
-    double *gsets = slots + nqs * slot_d;
+    double *gsets = tm + ((8 + nrs * 5 + NDM * NFRS + (qcap + 1) / 2 + nqs * slot_d + 1) & ~1);
 
     const int nbas = t.nbas;
     const int nao = t.nao;
@@ -331,14 +364,8 @@ rys_jk_warp_kernel(JKTask t)
                     pi[1] = ao_loc[qsh];
                 }
             }
-            double gout[NC][NFS];
-#pragma unroll
-            for (int n = 0; n < NC; ++n)
-#pragma unroll
-                for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
-            jkw_team_sync<TW>(team);
-
-            for (int pass = 0; pass < npass; ++pass) {
+            // phases 1-2 of one pass: roots/weights and 2D integrals of every g-set of the team
+            auto build_gsets = [&](const int pass) {
                 // ---------------- phase 1: roots and weights of every g-set ----------------
                 for (int it = lt; it < ngs * 2 * NROOTS; it += TEAM) {
                     const int g = it / (2 * NROOTS);
@@ -434,15 +461,20 @@ rys_jk_warp_kernel(JKTask t)
                             double v[LRS + 1];
 #pragma unroll
                             for (int f = 0; f <= LRS; ++f) v[f] = gg[f][ea];
+                            if (NCS == 1) {
+                                jkw_st_seg<LRS + 1>(o + (ea * (LQ + 1) + eb) * SUBP, v);
+                            } else {
+                                double seg[SUB];
 #pragma unroll
-                            for (int d = 0; d <= LS; ++d) {
+                                for (int d = 0; d <= LS; ++d) {
 #pragma unroll
-                                for (int c = 0; c <= LR; ++c)
-                                    o[(ea * (LQ + 1) + eb) * SUBP + c * (LS + 1) + d] = v[c];
-                                if (d < LS) {
+                                    for (int c = 0; c <= LR; ++c) seg[c * (LS + 1) + d] = v[c];
+                                    if (d < LS) {
 #pragma unroll
-                                    for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                                        for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                                    }
                                 }
+                                jkw_st_seg<SUB>(o + (ea * (LQ + 1) + eb) * SUBP, seg);
                             }
                         }
                         if (eb < LQ) {
@@ -454,122 +486,168 @@ rys_jk_warp_kernel(JKTask t)
                     }
                 }
                 jkw_team_sync<TW>(team);
-                // ---------------- phase 4: gout += gx * gy * gz ; digestion ----------------
-                for (int k = 0; k < K; ++k) {
-                    const double *gk = gsets + (k * NSW + s4) * GSET + 2 * NROOTS;
-                    if (lane_on) {
-                        if (NCS == 1) {
+            };
+            // phase 3: gout += gx * gy * gz over the roots of g-set g (register tile of this lane)
+            auto contract = [&](double (&gout)[NC][NFS], const int g) {
+                const double *gk = gsets + g * GSET + 2 * NROOTS;
+                const double cdx = rsgeom[0], cdy = rsgeom[1], cdz = rsgeom[2];
+                if (lane_on) {
+                    if (NCS == 1) {
 #pragma unroll
-                            for (int root = 0; root < NROOTS; ++root) {
-                                const double *gr = gk + root * 3 * GSIZEP;
-                                double gx[SUB], gy[SUB], gz[SUB];
+                        for (int root = 0; root < NROOTS; ++root) {
+                            const double *gr = gk + root * 3 * GSIZEP;
+                            double gx[SUB], gy[SUB], gz[SUB];
+                            {   // ket transfer (r <- s) of this lane's three bra-transferred rows
+                                double hx[LRS + 1], hy[LRS + 1], hz[LRS + 1];
+                                jkw_ld_seg<LRS + 1>(hx, gr + gbx);
+                                jkw_ld_seg<LRS + 1>(hy, gr + gby);
+                                jkw_ld_seg<LRS + 1>(hz, gr + gbz);
 #pragma unroll
-                                for (int i = 0; i < SUB; ++i) {
-                                    gx[i] = gr[gbx + i];
-                                    gy[i] = gr[gby + i];
-                                    gz[i] = gr[gbz + i];
-                                }
+                                for (int d = 0; d <= LS; ++d) {
 #pragma unroll
-                                for (int c = 0; c < NFR; ++c) {
+                                    for (int c = 0; c <= LR; ++c) {
+                                        gx[c * (LS + 1) + d] = hx[c];
+                                        gy[c * (LS + 1) + d] = hy[c];
+                                        gz[c * (LS + 1) + d] = hz[c];
+                                    }
+                                    if (d < LS) {
 #pragma unroll
-                                    for (int d = 0; d < NFS; ++d) {
-                                        gout[c][d] += gx[cart_x(LR, c) * (LS + 1) + cart_x(LS, d)]
-                                                    * gy[cart_y(LR, c) * (LS + 1) + cart_y(LS, d)]
-                                                    * gz[cart_z(LR, c) * (LS + 1) + cart_z(LS, d)];
+                                        for (int c = 0; c < LRS - d; ++c) {
+                                            hx[c] = hx[c + 1] + cdx * hx[c];
+                                            hy[c] = hy[c + 1] + cdy * hy[c];
+                                            hz[c] = hz[c + 1] + cdz * hz[c];
+                                        }
                                     }
                                 }
                             }
-                        } else {
-                            for (int root = 0; root < NROOTS; ++root) {
-                                const double *gr = gk + root * 3 * GSIZEP;
 #pragma unroll
-                                for (int n = 0; n < NC; ++n) {
-                                    double gx[LS + 1], gy[LS + 1], gz[LS + 1];
+                            for (int c = 0; c < NFR; ++c) {
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) {
+                                    gout[c][d] += gx[cart_x(LR, c) * (LS + 1) + cart_x(LS, d)]
+                                                * gy[cart_y(LR, c) * (LS + 1) + cart_y(LS, d)]
+                                                * gz[cart_z(LR, c) * (LS + 1) + cart_z(LS, d)];
+                                }
+                            }
+                        }
+                    } else {
+                        for (int root = 0; root < NROOTS; ++root) {
+                            const double *gr = gk + root * 3 * GSIZEP;
+#pragma unroll
+                            for (int n = 0; n < NC; ++n) {
+                                double gx[LS + 1], gy[LS + 1], gz[LS + 1];
+                                if ((LS + 1) % 2 == 0) {
+                                    jkw_ld_seg<LS + 1>(gx, gr + gbx + ox[n]);
+                                    jkw_ld_seg<LS + 1>(gy, gr + gby + oy[n]);
+                                    jkw_ld_seg<LS + 1>(gz, gr + gbz + oz[n]);
+                                } else {
 #pragma unroll
                                     for (int i = 0; i <= LS; ++i) {
                                         gx[i] = gr[gbx + ox[n] + i];
                                         gy[i] = gr[gby + oy[n] + i];
                                         gz[i] = gr[gbz + oz[n] + i];
                                     }
+                                }
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) {
+                                    gout[n][d] += gx[cart_x(LS, d)] * gy[cart_y(LS, d)] * gz[cart_z(LS, d)];
+                                }
+                            }
+                        }
+                    }
+                }
+            };
+            // J/K digestion of quartet slot j with this lane's tile (reference: rys_contract_jk.cu:304-329)
+            auto digest = [&](double (&gout)[NC][NFS], const int j) {
+                if (lane_on && j < nb) {
+                    const double *sl = slots + j * slot_d;
+                    const int *pi = (const int *)(sl + 7);
+                    const int p0 = pi[0];
+                    const int q0 = pi[1];
+                    const size_t prow = (size_t)(p0 + a) * nao;
+                    const size_t qrow = (size_t)(q0 + b) * nao;
+#pragma unroll
+                    for (int idm = 0; idm < NDM; ++idm) {
+                        const double *dm = t.dm + idm * nao2;
+                        if (do_j) {
+                            double *vj = t.vj + idm * nao2;
+                            double dpq = __ldg(dm + prow + q0 + b);
+                            double s = 0.;
+#pragma unroll
+                            for (int n = 0; n < NC; ++n) {
+                                if (c0 + n < NFR) {
 #pragma unroll
                                     for (int d = 0; d < NFS; ++d) {
-                                        gout[n][d] += gx[cart_x(LS, d)] * gy[cart_y(LS, d)] * gz[cart_z(LS, d)];
+                                        s += gout[n][d] * drs[idm * NFRS + (c0 + n) * NFS + d];
+                                        jacc[idm][n][d] += gout[n][d] * dpq;
                                     }
                                 }
+                            }
+                            JK_ATOMIC_ADD(vj + prow + q0 + b, s);
+                        }
+                        if (do_k) {
+                            double *vk = t.vk + idm * nao2;
+                            double dqs[NFS], dps[NFS], kps[NFS], kqs[NFS];
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) {
+                                dqs[d] = __ldg(dm + qrow + s0 + d);
+                                dps[d] = __ldg(dm + prow + s0 + d);
+                                kps[d] = 0.;
+                                kqs[d] = 0.;
+                            }
+#pragma unroll
+                            for (int n = 0; n < NC; ++n) {
+                                if (c0 + n < NFR) {
+                                    double dqr = __ldg(dm + qrow + r0 + c0 + n);
+                                    double dpr = __ldg(dm + prow + r0 + c0 + n);
+                                    double kpr = 0., kqr = 0.;
+#pragma unroll
+                                    for (int d = 0; d < NFS; ++d) {
+                                        double gv = gout[n][d];
+                                        kpr += gv * dqs[d];
+                                        kqr += gv * dps[d];
+                                        kps[d] += gv * dqr;
+                                        kqs[d] += gv * dpr;
+                                    }
+                                    JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr);
+                                    JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr);
+                                }
+                            }
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) {
+                                JK_ATOMIC_ADD(vk + prow + s0 + d, kps[d]);
+                                JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
                             }
                         }
                     }
-                    const bool dig = single || (pass == npass - 1 && k == K - 1);
-                    if (!dig) continue;
-                    const int j = single ? k * NSW + s4 : s4;
-                    if (lane_on && j < nb) {
-                        const double *sl = slots + j * slot_d;
-                        const int *pi = (const int *)(sl + 7);
-                        const int p0 = pi[0];
-                        const int q0 = pi[1];
-                        const size_t prow = (size_t)(p0 + a) * nao;
-                        const size_t qrow = (size_t)(q0 + b) * nao;
-#pragma unroll
-                        for (int idm = 0; idm < NDM; ++idm) {
-                            const double *dm = t.dm + idm * nao2;
-                            if (do_j) {
-                                double *vj = t.vj + idm * nao2;
-                                double dpq = __ldg(dm + prow + q0 + b);
-                                double s = 0.;
-#pragma unroll
-                                for (int n = 0; n < NC; ++n) {
-                                    if (c0 + n < NFR) {
-#pragma unroll
-                                        for (int d = 0; d < NFS; ++d) {
-                                            s += gout[n][d] * drs[idm * NFRS + (c0 + n) * NFS + d];
-                                            jacc[idm][n][d] += gout[n][d] * dpq;
-                                        }
-                                    }
-                                }
-                                JK_ATOMIC_ADD(vj + prow + q0 + b, s);
-                            }
-                            if (do_k) {
-                                double *vk = t.vk + idm * nao2;
-                                double dqs[NFS], dps[NFS], kps[NFS], kqs[NFS];
-#pragma unroll
-                                for (int d = 0; d < NFS; ++d) {
-                                    dqs[d] = __ldg(dm + qrow + s0 + d);
-                                    dps[d] = __ldg(dm + prow + s0 + d);
-                                    kps[d] = 0.;
-                                    kqs[d] = 0.;
-                                }
-#pragma unroll
-                                for (int n = 0; n < NC; ++n) {
-                                    if (c0 + n < NFR) {
-                                        double dqr = __ldg(dm + qrow + r0 + c0 + n);
-                                        double dpr = __ldg(dm + prow + r0 + c0 + n);
-                                        double kpr = 0., kqr = 0.;
-#pragma unroll
-                                        for (int d = 0; d < NFS; ++d) {
-                                            double gv = gout[n][d];
-                                            kpr += gv * dqs[d];
-                                            kqr += gv * dps[d];
-                                            kps[d] += gv * dqr;
-                                            kqs[d] += gv * dpr;
-                                        }
-                                        JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr);
-                                        JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr);
-                                    }
-                                }
-#pragma unroll
-                                for (int d = 0; d < NFS; ++d) {
-                                    JK_ATOMIC_ADD(vk + prow + s0 + d, kps[d]);
-                                    JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
-                                }
-                            }
-                        }
-                    }
+                }
+            };
+            jkw_team_sync<TW>(team);
+            if (single) {
+                // K different quartets per lane slot, one primitive quartet each
+                build_gsets(0);
+                for (int k = 0; k < K; ++k) {
+                    double gout[NC][NFS];
 #pragma unroll
                     for (int n = 0; n < NC; ++n)
 #pragma unroll
                         for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
+                    contract(gout, k * NSW + s4);
+                    digest(gout, k * NSW + s4);
                 }
-            }   // passes
+            } else {
+                // contracted class: K primitive quartets of the same quartet per pass
+                double gout[NC][NFS];
+#pragma unroll
+                for (int n = 0; n < NC; ++n)
+#pragma unroll
+                    for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
+                for (int pass = 0; pass < npass; ++pass) {
+                    build_gsets(pass);
+                    for (int k = 0; k < K; ++k) contract(gout, k * NSW + s4);
+                }
+                digest(gout, s4);
+            }
 
             // ---------------- keep the unprocessed remainder of the queue ----------------
             jkw_team_sync<TW>(team);

@@ -97,6 +97,8 @@ class _VHFOpt:
         # set to a dict to collect per-class kernel times (ms), like the
         # reference's _TimingCollector (jk.py:1170-1188); costs a sync per class
         self.class_timing = None
+        self.n_streams = 4
+        self._streams = None
 
     def reset(self, mol):
         self.mol = mol
@@ -203,6 +205,15 @@ class _VHFOpt:
             with_j = False
         envs = self._rys_envs
         stream = loader.current_stream_ptr()
+        # Class launches are independent (they only meet in the J/K atomics), so
+        # they are dealt over a few side streams: the tail of one launch, when
+        # most SMs have run out of work items, overlaps the start of the next.
+        side = None
+        if dev.type == 'cuda' and self.class_timing is None and self.n_streams > 1:
+            if self._streams is None:
+                self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams)]
+            side = self._streams
+            main = torch.cuda.current_stream()
 
         dm_cond = torch.empty((nbas, nbas), dtype=torch.float32, device=dev)
         err = lib.B200_condense(_ptr(dm_cond), _ptr(dms), ndm_k, nao, _ptr(envs._keep[3]), nbas, stream)
@@ -217,6 +228,11 @@ class _VHFOpt:
         if getattr(self, 'counter', None) is not None:
             self._counter_last = int(self.counter.item())
         heads = torch.zeros(len(tasks) + 1, dtype=torch.int32, device=dev)
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for st in side:
+                st.wait_event(ev)
         rank, world = self._partition()
         uniq = smol.uniq_l_ctr
         lprim = (ctypes.c_int * 8)()
@@ -240,6 +256,8 @@ class _VHFOpt:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            if side is not None:
+                stream = ctypes.c_void_p(side[it % len(side)].cuda_stream)
             err = lib.B200_build_jk_class(
                 _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
                 _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
@@ -258,6 +276,12 @@ class _VHFOpt:
                     n = int(self.counter.item())
                     rec[3] += n - self._counter_last
                     self._counter_last = n
+
+        if side is not None:
+            for st in side:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
 
         if world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
             # one collective per build over the concatenated [vj|vk] partials

@@ -17,6 +17,7 @@ ap.add_argument('--classes', default='')       # "2,2,2,2;2,1,2,1"
 ap.add_argument('--top', type=int, default=30)
 ap.add_argument('--out', default=None)
 ap.add_argument('--beta', type=float, default=0.8)
+ap.add_argument('--detail', default=None, help='json: one row per (l, nprim) launch')
 args = ap.parse_args()
 xyz = os.path.join(ROOT, 'gpu4pyscf_b200', 'data', 'molecules', args.mol + '.xyz')
 mol = M(atom=read_xyz(xyz), basis=args.basis)
@@ -50,6 +51,9 @@ print('variant', os.environ.get('GPU4PYSCF_B200_VARIANT'), 'total %.1f ms (wall 
 rows = sorted(agg.items(), key=lambda kv: -kv[1][0])
 for k, a in rows[:args.top]:
     print('  (%d%d|%d%d) %9.2f ms %5.1f%%  quartets %.3e  %7.3f TF/s' % (*k, a[0], 100 * a[0] / tot_ms, a[1], a[2] / max(a[0], 1e-9) / 1e9))
+if args.detail:
+    json.dump([{'lprim': list(k), 'ms': v[0], 'npx': v[1], 'npy': v[2], 'quartets': v[3], 'flops': v[3] * flops.f_quartet(k)}
+               for k, v in opt.class_timing.items()], open(args.detail, 'w'))
 if args.out:
     json.dump({'total_ms': tot_ms, 'quartets': tot_q, 'f_alg': tot_fl,
                'classes': {str(k): a for k, a in rows}}, open(args.out, 'w'))
