@@ -104,8 +104,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         fprintf(stderr, "rys_jk: more than %d primitive pairs per shell pair\n", JK_MAXPP);
         return 1;
     }
-    const int nteams = JKW_MAXTHREADS / C::TEAM;
-    const int nt = nteams * C::TEAM;
+    int nteams = JKW_MAXTHREADS / C::TEAM;
     const int nprimq = npq * nrs;
     // g-sets per lane slot: fill (not overfill) the team in the recurrence phase,
     // whose work items are (g-set, root, axis)
@@ -120,6 +119,8 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     };
     const int budget = (smem_max + 1024) / minb - 1024;
     while (K > 1 && smem_of(K) > budget) --K;
+    while (nteams > 1 && smem_of(K) > smem_max) --nteams;     // fewer teams per block for the fattest classes
+    const int nt = nteams * C::TEAM;
     int smem = smem_of(K);
     if (smem > smem_max) {
         fprintf(stderr, "rys_jk_warp: class (%d%d|%d%d) needs %d B of shared memory\n", LP, LQ, LR, LS, smem);

@@ -16,6 +16,9 @@
 // resident blocks per SM requested from the register allocator, by class size
 __host__ __device__ constexpr int jkt_minblocks(int nf_total)
 {
+#ifdef JKT_MINBLOCKS_FIXED
+    return JKT_MINBLOCKS_FIXED;
+#endif
     return nf_total <= 12 ? 5 : (nf_total <= 40 ? 4 : (nf_total <= 70 ? 3 : 2));
 }
 

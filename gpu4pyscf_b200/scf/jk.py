@@ -238,8 +238,11 @@ class _VHFOpt:
         lprim = (ctypes.c_int * 8)()
         only = getattr(self, 'only_classes', None)   # measurement: restrict to some classes
         for it, (ky, kx, dedupe) in enumerate(tasks):
-            if only is not None and (tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 0])) not in only:
-                continue
+            if only is not None:
+                l4 = tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 0])
+                p4 = tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 1])
+                if l4 not in only and l4 + p4 not in only:
+                    continue
             pair_x, q_x = self.bas_pair_cache[kx][:2]
             pair_y, q_y = self.bas_pair_cache[ky][:2]
             if len(pair_x) == 0 or len(pair_y) == 0:
