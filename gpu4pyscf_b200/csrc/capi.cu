@@ -94,7 +94,7 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const uint32_t *pair_x, const float *q_x, int npair_x,
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
-                        int dedupe, int rank, int world, int *head, void *stream)
+                        int dedupe, int rank, int world, int *head, void *stream, const double *rec_y)
 {
     if (npair_x <= 0 || npair_y <= 0) return 0;
     if (RYS_b200_init()) return 1;
@@ -120,6 +120,8 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
     t.q_margin = q_margin;
     t.dedupe = dedupe;
     t.head = head;
+    t.rec_y = rec_y;
+    t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
     t.rank = rank;
     t.world = world < 1 ? 1 : world;
     t.nprim_p = lprim[4]; t.nprim_q = lprim[5]; t.nprim_r = lprim[6]; t.nprim_s = lprim[7];
@@ -182,13 +184,13 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
         return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
                                    pair_kl_mapping, q_cond_kl, npairs_kl,
                                    pair_ij_mapping, q_cond_ij, npairs_ij,
-                                   dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr);
+                                   dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr, nullptr);
     } else {
         int lprim[8] = {lk, ll, li, lj, nk, nl, ni, nj};
         return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
                                    pair_ij_mapping, q_cond_ij, npairs_ij,
                                    pair_kl_mapping, q_cond_kl, npairs_kl,
-                                   dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr);
+                                   dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr, nullptr);
     }
 }
 
@@ -208,6 +210,20 @@ int B200_qcond(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, i
 #undef QC
     fprintf(stderr, "B200_qcond: unsupported pair type (%d,%d)\n", li, lj);
     return 1;
+}
+
+int B200_pair_rec_stride(int nprim_i, int nprim_j) { return pair_rec_stride(nprim_i * nprim_j); }
+
+int B200_pair_records(double *out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,
+                      int nprim_i, int nprim_j, void *stream)
+{
+    if (npairs <= 0) return 0;
+    int nt = 128;
+    int grid = (npairs + nt - 1) / nt;
+    KLAUNCH(pair_record_kernel, grid, nt, 0, (cudaStream_t)stream, out, pairs, npairs,
+            (const int *)envs->bas, (const double *)envs->env, (const int *)envs->ao_loc, envs->nbas,
+            nprim_i, nprim_j);
+    return rt_last_error("pair_record_kernel");
 }
 
 int B200_condense(float *out, const double *dm, int n_dm, int nao, const int *ao_loc, int nbas,

@@ -68,9 +68,17 @@ struct JKTask {
     unsigned long long *counter;  // optional: number of quartets evaluated (measurement)
     int nq;                 // quartet slots per block
     int slot_doubles;       // shared-memory doubles per slot
+    const double *rec_y;    // optional per-pair records of the Y list (pair_record_kernel), or null
+    int rec_stride;         // doubles per record
     int ychunk;             // work item = (X pair, chunk of `ychunk` consecutive Y candidates)
     int nychunk;            // ceil(npair_y / ychunk)
 };
+
+// Per-pair record (precomputed once per _VHFOpt.build, in pair-list order):
+//   [0..2] A-B, [3..5] A, [6] (int p0, int q0) AO offsets, [7] 0.5 if ish == jsh else 1,
+//   then per primitive pair: zeta, Px, Py, Pz, ci*cj*exp(-ai*aj/zeta*|AB|^2)
+#define PAIR_REC_HDR 8
+__host__ __device__ inline int pair_rec_stride(int npq) { return (PAIR_REC_HDR + 5 * npq + 1) & ~1; }
 
 // ---- Cartesian component tables (lexical order xx, xy, xz, yy, yz, zz ...;
 // same convention as libcint / the reference's rys_constant.cu:21-112, but

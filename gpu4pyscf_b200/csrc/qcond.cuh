@@ -101,3 +101,46 @@ __global__ void qcond_kernel(float *q_out, const uint32_t *pairs, int npairs,
         for (int b = 0; b < NFJ; ++b) vmax = fmax(vmax, fabs(val[a][b]));
     q_out[n] = vmax > 1e-300 ? (float)(.5 * log(vmax)) : -700.f;
 }
+
+// One thread per shell pair: Gaussian-product data of all primitive pairs, so that
+// the J/K kernels read one contiguous record per streamed pair instead of chasing
+// bas/env pointers (replaces nothing in the reference, whose kernels recompute
+// these per quartet, rys_contract_jk.cu:146-160; it plays the role the reference
+// reserves for bas_pair_cache extensions).
+__global__ void pair_record_kernel(double *out, const uint32_t *pairs, int npairs,
+                                   const int *bas, const double *env, const int *ao_loc, int nbas,
+                                   int nprim_i, int nprim_j)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npairs) return;
+    const uint32_t pij = pairs[n];
+    const int ish = pij / nbas;
+    const int jsh = pij - ish * nbas;
+    const double *Ri = env + bas[ish * BAS_SLOTS + PTR_BAS_COORD];
+    const double *Rj = env + bas[jsh * BAS_SLOTS + PTR_BAS_COORD];
+    const double *ei = env + bas[ish * BAS_SLOTS + PTR_EXP];
+    const double *ej = env + bas[jsh * BAS_SLOTS + PTR_EXP];
+    const double *ci = env + bas[ish * BAS_SLOTS + PTR_COEFF];
+    const double *cj = env + bas[jsh * BAS_SLOTS + PTR_COEFF];
+    double *rec = out + (size_t)n * pair_rec_stride(nprim_i * nprim_j);
+    const double dx = Ri[0] - Rj[0], dy = Ri[1] - Rj[1], dz = Ri[2] - Rj[2];
+    const double rr2 = dx * dx + dy * dy + dz * dz;
+    rec[0] = dx; rec[1] = dy; rec[2] = dz;
+    rec[3] = Ri[0]; rec[4] = Ri[1]; rec[5] = Ri[2];
+    int *pi = (int *)(rec + 6);
+    pi[0] = ao_loc[ish];
+    pi[1] = ao_loc[jsh];
+    rec[7] = ish == jsh ? .5 : 1.;
+    for (int ip = 0; ip < nprim_i; ++ip)
+        for (int jp = 0; jp < nprim_j; ++jp) {
+            const double ai = ei[ip], aj = ej[jp];
+            const double zeta = ai + aj;
+            const double f = aj / zeta;
+            double *o = rec + PAIR_REC_HDR + (ip * nprim_j + jp) * 5;
+            o[0] = zeta;
+            o[1] = Ri[0] - f * dx;
+            o[2] = Ri[1] - f * dy;
+            o[3] = Ri[2] - f * dz;
+            o[4] = ci[ip] * cj[jp] * exp(-ai * f * rr2);
+        }
+}

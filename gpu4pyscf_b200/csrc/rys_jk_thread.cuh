@@ -182,36 +182,62 @@ rys_jk_thread_kernel(JKTask t)
 
             if (lane < nb) {
                 const int iy = queue[lane];
-                const uint32_t pair_pq = t.pair_y[iy];
-                const int psh = pair_pq / nbas;
-                const int qsh = pair_pq - psh * nbas;
-                const int p0 = ao_loc[psh];
-                const int q0 = ao_loc[qsh];
-                const double *Rp = env + bas[psh * BAS_SLOTS + PTR_BAS_COORD];
-                const double *Rq = env + bas[qsh * BAS_SLOTS + PTR_BAS_COORD];
-                const double *ep = env + bas[psh * BAS_SLOTS + PTR_EXP];
-                const double *eq = env + bas[qsh * BAS_SLOTS + PTR_EXP];
-                const double *cp = env + bas[psh * BAS_SLOTS + PTR_COEFF];
-                const double *cq = env + bas[qsh * BAS_SLOTS + PTR_COEFF];
-                const double Ax = Rp[0], Ay = Rp[1], Az = Rp[2];
-                const double ABx = Ax - Rq[0], ABy = Ay - Rq[1], ABz = Az - Rq[2];
-                const double rr2 = ABx * ABx + ABy * ABy + ABz * ABz;
-                double fac = PI_FAC;
-                if (psh == qsh) fac *= .5;
+                // Gaussian products of the Y pair: from its precomputed record when the
+                // caller provides one, else from bas/env (reference-signature entry)
+                const double *rec = t.rec_y != nullptr ? t.rec_y + (size_t)iy * t.rec_stride : nullptr;
+                int p0, q0;
+                double Ax, Ay, Az, ABx, ABy, ABz, fac = PI_FAC, rr2 = 0.;
+                const double *ep = nullptr, *eq = nullptr, *cp = nullptr, *cq = nullptr;
+                if (rec != nullptr) {
+                    const double2 h0 = *(const double2 *)(rec + 0);
+                    const double2 h1 = *(const double2 *)(rec + 2);
+                    const double2 h2 = *(const double2 *)(rec + 4);
+                    const double2 h3 = *(const double2 *)(rec + 6);
+                    ABx = h0.x; ABy = h0.y; ABz = h1.x;
+                    Ax = h1.y; Ay = h2.x; Az = h2.y;
+                    p0 = ((const int *)&h3.x)[0];
+                    q0 = ((const int *)&h3.x)[1];
+                    fac *= h3.y;                               // 1/2 when psh == qsh
+                    if (t.dedupe == 1 && iy == ix) fac *= .5;  // same list: (pq) == (rs)
+                } else {
+                    const uint32_t pair_pq = t.pair_y[iy];
+                    const int psh = pair_pq / nbas;
+                    const int qsh = pair_pq - psh * nbas;
+                    p0 = ao_loc[psh];
+                    q0 = ao_loc[qsh];
+                    const double *Rp = env + bas[psh * BAS_SLOTS + PTR_BAS_COORD];
+                    const double *Rq = env + bas[qsh * BAS_SLOTS + PTR_BAS_COORD];
+                    ep = env + bas[psh * BAS_SLOTS + PTR_EXP];
+                    eq = env + bas[qsh * BAS_SLOTS + PTR_EXP];
+                    cp = env + bas[psh * BAS_SLOTS + PTR_COEFF];
+                    cq = env + bas[qsh * BAS_SLOTS + PTR_COEFF];
+                    Ax = Rp[0]; Ay = Rp[1]; Az = Rp[2];
+                    ABx = Ax - Rq[0]; ABy = Ay - Rq[1]; ABz = Az - Rq[2];
+                    rr2 = ABx * ABx + ABy * ABy + ABz * ABz;
+                    if (psh == qsh) fac *= .5;
+                    if (pair_pq == pair_rs) fac *= .5;
+                }
                 if (rsh == ssh) fac *= .5;
-                if (pair_pq == pair_rs) fac *= .5;
 
                 double gout[NFPQ * NFRS];
 #pragma unroll
                 for (int n = 0; n < NFPQ * NFRS; ++n) gout[n] = 0.;
 
-                for (int ip = 0; ip < t.nprim_p; ++ip) {
-                for (int iq = 0; iq < t.nprim_q; ++iq) {
-                    const double ap = ep[ip], aq = eq[iq];
-                    const double zeta = ap + aq;
-                    const double fq = aq / zeta;
-                    const double Px = Ax - fq * ABx, Py = Ay - fq * ABy, Pz = Az - fq * ABz;
-                    const double cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
+                for (int ipq = 0; ipq < npq; ++ipq) {
+                    double zeta, Px, Py, Pz, cpq;
+                    if (rec != nullptr) {
+                        const double *pr = rec + PAIR_REC_HDR + ipq * 5;
+                        zeta = pr[0]; Px = pr[1]; Py = pr[2]; Pz = pr[3];
+                        cpq = fac * pr[4];
+                    } else {
+                        const int ip = ipq / t.nprim_q;
+                        const int iq = ipq - ip * t.nprim_q;
+                        const double ap = ep[ip], aq = eq[iq];
+                        zeta = ap + aq;
+                        const double fq = aq / zeta;
+                        Px = Ax - fq * ABx; Py = Ay - fq * ABy; Pz = Az - fq * ABz;
+                        cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
+                    }
                     for (int irs = 0; irs < nrs; ++irs) {
                         const double *rr = rsprim + irs * 5;
                         const double eta = rr[0];
@@ -312,7 +338,7 @@ rys_jk_thread_kernel(JKTask t)
                             }
                         }
                     }
-                } }
+                }
 
                 // ---------------- digestion (thread-local) ----------------
 #pragma unroll

@@ -328,6 +328,24 @@ rys_jk_warp_kernel(JKTask t)
                 const int ip = i - j * npq;
                 const bool active = j < nb;
                 const int iy = queue[active ? j : 0];
+                double *sl = slots + j * slot_d;
+                double *o = sl + JKW_SLOT_HDR + ip * 5;
+                if (t.rec_y != nullptr) {
+                    // precomputed record of the pair (B200_pair_records)
+                    const double *rec = t.rec_y + (size_t)iy * t.rec_stride;
+                    const double *pr = rec + PAIR_REC_HDR + ip * 5;
+                    o[0] = pr[0]; o[1] = pr[1]; o[2] = pr[2]; o[3] = pr[3]; o[4] = pr[4];
+                    if (ip == 0) {
+                        sl[0] = rec[0]; sl[1] = rec[1]; sl[2] = rec[2];
+                        sl[3] = rec[3]; sl[4] = rec[4]; sl[5] = rec[5];
+                        double fac = PI_FAC * rec[7];
+                        if (rsh == ssh) fac *= .5;
+                        if (t.dedupe == 1 && iy == ix) fac *= .5;
+                        sl[6] = active ? fac : 0.;
+                        sl[7] = rec[6];                    // (p0, q0)
+                    }
+                    continue;
+                }
                 const uint32_t pair_pq = t.pair_y[iy];
                 const int psh = pair_pq / nbas;
                 const int qsh = pair_pq - psh * nbas;
@@ -344,8 +362,6 @@ rys_jk_warp_kernel(JKTask t)
                 double ap = ep[ipp], aq = eq[iq];
                 double zeta = ap + aq;
                 double f = aq / zeta;
-                double *sl = slots + j * slot_d;
-                double *o = sl + JKW_SLOT_HDR + ip * 5;
                 o[0] = zeta;
                 o[1] = Rp[0] - f * dx;
                 o[2] = Rp[1] - f * dy;

@@ -245,6 +245,7 @@ class _VHFOpt:
                     continue
             pair_x, q_x = self.bas_pair_cache[kx][:2]
             pair_y, q_y = self.bas_pair_cache[ky][:2]
+            rec_y = self.bas_pair_cache[ky][3]
             if len(pair_x) == 0 or len(pair_y) == 0:
                 continue
             # cheap class-level early exit
@@ -264,7 +265,7 @@ class _VHFOpt:
             err = lib.B200_build_jk_class(
                 _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
                 _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
-                _ptr(dm_cond), cutoff, dm_penalty, 0., dedupe, rank, world, head, stream)
+                _ptr(dm_cond), cutoff, dm_penalty, 0., dedupe, rank, world, head, stream, _ptr(rec_y))
             if err:
                 raise RuntimeError('B200_build_jk_class failed for class %s' % (tuple(lprim),))
             if self.class_timing is not None and dev.type == 'cuda':
@@ -366,5 +367,11 @@ def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib):
         order = torch.argsort(q, descending=True, stable=True)
         ids = ids[order].contiguous()
         q = q[order].contiguous()
-        cache[key] = (ids, q, q)
+        # Gaussian-product records of the pairs, in list order
+        npi, npj = int(uniq[key[0], 1]), int(uniq[key[1], 1])
+        rec = torch.empty(len(ids) * lib.B200_pair_rec_stride(npi, npj), dtype=torch.float64, device=device)
+        err = lib.B200_pair_records(_ptr(rec), ctypes.byref(rys_envs), _ptr(ids), len(ids), npi, npj, stream)
+        if err:
+            raise RuntimeError('B200_pair_records failed')
+        cache[key] = (ids, q, q, rec)
     return cache

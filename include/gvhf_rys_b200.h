@@ -72,19 +72,29 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
  *   q_margin: 0 for exactly sorted q_y, 4 for the reference's binned order.
  *   rank/world: X pairs ix with ix % world == rank are processed (multi-GPU
  *   partition of the q-sorted list); head: zeroed device int work counter.
+ *   rec_y: optional per-pair records of the Y list (B200_pair_records), NULL to
+ *   derive the Gaussian products from bas/env inside the kernel.
  * vj or vk may be NULL (K-only / J-only).  n_dm is arbitrary. */
 int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
                         const RysIntEnvVars *envs, const int *lprim,
                         const uint32_t *pair_x, const float *q_x, int npair_x,
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
-                        int dedupe, int rank, int world, int *head, void *stream);
+                        int dedupe, int rank, int world, int *head, void *stream, const double *rec_y);
 
 /* 1 if a kernel is instantiated with (lp,lq) as the lane side (Y) and (lr,ls)
  * as the register-tile side (X); exactly one orientation of every unordered
  * angular class exists.  Plays the role of the reference's kernel-selection
  * switch (rys_contract_jk.cu:395-440). */
 int B200_has_class(int lp, int lq, int lr, int ls);
+
+/* Per-pair Gaussian-product records for a pair list of one (nprim_i, nprim_j) class,
+ * B200_pair_rec_stride() doubles each, in list order (layout: csrc/common.cuh).  The
+ * reference recomputes these per quartet (rys_contract_jk.cu:146-160); precomputing
+ * them once per _VHFOpt.build is what its bas_pair_cache exists for (scf/jk.py:1040-1120). */
+int B200_pair_rec_stride(int nprim_i, int nprim_j);
+int B200_pair_records(double *out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,
+                      int nprim_i, int nprim_j, void *stream);
 
 /* Schwarz bounds q = 1/2 log max|(ij|ij)| for a list of shell pairs of one
  * (li, lj, nprim_i, nprim_j) class.  Replaces int2e_qcond_estimator,

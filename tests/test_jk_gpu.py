@@ -151,8 +151,8 @@ def test_reference_signature_entry():
         for j in range(i + 1):
             for k in range(i + 1):
                 for l in range(k + 1):
-                    pij, qij, _ = opt.bas_pair_cache[i, j]
-                    pkl, qkl, _ = opt.bas_pair_cache[k, l]
+                    pij, qij = opt.bas_pair_cache[i, j][:2]
+                    pkl, qkl = opt.bas_pair_cache[k, l][:2]
                     shls = (ctypes.c_int * 8)(offs[i], offs[i + 1], offs[j], offs[j + 1],
                                               offs[k], offs[k + 1], offs[l], offs[l + 1])
                     err = lib.RYS_build_jk(

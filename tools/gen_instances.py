@@ -53,6 +53,60 @@ def warp_cfg(y, x, ndm):
 
 
 WARP_KERNEL = os.environ.get('B200_WARP_KERNEL', '1') == '1'
+CHOOSER = os.environ.get('B200_CHOOSER', 'cost')
+REG_DOUBLES = int(os.environ.get('B200_REG_DOUBLES', '180'))
+
+
+def warp_cfg_cost(y, x, ndm):
+    """Instruction-count model: estimated warp instructions per quartet for lanes =
+    Y pair, register tile = X pair (split NCS ways); returns (-cost, ncs) so that
+    larger is better, like warp_cfg."""
+    import math
+    lp, lq = y
+    lr, ls = x
+    nfpq = nf(lp) * nf(lq)
+    nfr, nfs = nf(lr), nf(ls)
+    lpq, lrs = lp + lq, lr + ls
+    nroots = (lpq + lrs) // 2 + 1
+    sub = (lr + 1) * (ls + 1)
+    best = None
+    for ncs in range(1, nfr + 1):
+        nc = -(-nfr // ncs)
+        if -(-nfr // nc) != ncs:
+            continue
+        tile = nc * nfs
+        g = nfpq * ncs
+        if g > 256:
+            break
+        tw = -(-g // 32)
+        nsw = 32 // g if tw == 1 else 1
+        seg = lrs + 1 if ncs == 1 else sub
+        regs = tile * (1 + ndm) + (3 * sub + 3 * seg if ncs == 1 else 3 * (ls + 1))
+        if regs > REG_DOUBLES:
+            continue
+        ld = 3 * ((seg + 1) // 2) if ncs == 1 else 3 * (ls + 1) * nc
+        hrr = 3 * sum(lrs - d for d in range(ls)) if ncs == 1 else 0
+        dig = 6 * tile * ndm + 3 * (2 * nc + 2 * nfs + 1) * ndm
+        w = nroots * (ld + hrr + 2 * tile) + dig + 20
+        k = max(1, min(4, (32 * tw) // (nsw * 3 * nroots)))
+        nab2 = (lp + 1) * (lq + 1)
+        p2 = 60 + 3 * (lpq + 1) * (lrs + 1) + nab2 * ((seg + 1) // 2 + 2)
+        f = (150 + 100 * math.ceil(2 * nroots * nsw * k / (32 * tw))
+             + p2 * math.ceil(3 * nroots * nsw * k / (32 * tw)) + 100)
+        cost = tw * (f / k + w) / nsw * (1.6 if tw > 1 else 1.)   # named-barrier teams measured slower than modelled
+        if best is None or -cost > best[0]:
+            best = (-cost, ncs)
+    return best
+
+
+
+_warp_cfg_score = warp_cfg
+
+
+def warp_cfg(y, x, ndm):
+    if CHOOSER == 'cost':
+        return warp_cfg_cost(y, x, ndm)
+    return _warp_cfg_score(y, x, ndm)
 
 
 def classes():
@@ -104,7 +158,7 @@ def main(dst):
                         decls.append((lp, lq, lr, ls, ndm, name))
                         continue
                     wc = warp_cfg((lp, lq), (lr, ls), ndm) if WARP_KERNEL else None
-                    if wc is not None and wc[0] >= 0.3:
+                    if wc is not None and (CHOOSER == 'cost' or wc[0] >= 0.3):
                         f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
                                 '{ return jk_launch_warp<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
                                 % (name, lp, lq, lr, ls, wc[1], ndm))
