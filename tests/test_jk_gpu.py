@@ -168,3 +168,91 @@ def test_reference_signature_entry():
     vk = vk + vk.transpose(1, 2)
     assert abs(vj - ref_vj).max() < 1e-10
     assert abs(vk - ref_vk).max() < 1e-10
+
+
+def _taxol(natoms=None, basis='def2-tzvp'):
+    import os
+    from gpu4pyscf_b200.gto.mole import M, read_xyz
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    xyz = read_xyz(os.path.join(root, 'gpu4pyscf_b200', 'data', 'molecules', '113_Taxol.xyz'))
+    if natoms:
+        xyz = '\n'.join(xyz.splitlines()[:natoms])
+    return M(atom=xyz, basis=basis)
+
+
+def _decaying_density(mol, seed=0, beta=0.8):
+    rng = np.random.RandomState(seed)
+    nao = mol.nao
+    ao_atom = np.repeat(mol._bas[:, 0], np.diff(mol.ao_loc_nr()))
+    R = mol.atom_coords()
+    dist = np.linalg.norm(R[ao_atom][:, None] - R[ao_atom][None], axis=-1)
+    d = (rng.rand(nao, nao) - .5) * np.exp(-beta * dist)
+    return d + d.T + np.eye(nao)
+
+
+def test_qcond_matches_oracle():
+    """Schwarz bounds of B200_qcond (through _VHFOpt.build) against the oracle's
+    sqrt(max|(ij|ij)|); the stored value is 1/2 log of the same maximum (float32)."""
+    from gpu4pyscf_b200.scf import jk
+    oracle = _oracle()
+    mol = molecules.water('def2-tzvp')
+    opt = jk._VHFOpt(mol).build()
+    smol = opt.sorted_mol
+    q_ref = oracle.q_cond(smol)                     # sorted, decontracted Cartesian shells
+    nbas = smol.nbas
+    n = 0
+    for key, val in opt.bas_pair_cache.items():
+        ids, q = val[0].cpu().numpy().astype(np.int64), val[1].cpu().numpy()
+        ish, jsh = ids // nbas, ids % nbas
+        ref = np.log(q_ref[ish, jsh])
+        assert abs(q - ref).max() < 2e-5, (key, abs(q - ref).max())
+        n += len(ids)
+    assert n > 100
+
+
+def test_fragment_with_screening_matches_oracle():
+    """8-atom Taxol fragment / def2-TZVP with a decaying density, so that the Schwarz +
+    density screening, the q-sorted early exit and the Y-chunk work items are all active;
+    oracle evaluated WITHOUT screening.  Tolerance 1e-10 (BASELINE.json north_star)."""
+    mol = _taxol(8)
+    dm = _decaying_density(mol)
+    _check(mol, dm, 1, tol=1e-10)
+
+
+def test_full_size_properties():
+    """Taxol / def2-TZVP (BASELINE.json configs[2], 2228 AOs): size-independent properties
+    of J/K -- symmetry, linearity in D, the exchange of densities
+    tr(D1 J[D2]) = tr(D2 J[D1]) (same for K), and invariance to the multi-GPU partition
+    (two half builds, ranks 0 and 1 of 2, sum to the full build)."""
+    from gpu4pyscf_b200.scf import jk
+    mol = _taxol()
+    nao = mol.nao
+    d1 = torch.as_tensor(_decaying_density(mol, 0), device='cuda')
+    d2 = torch.as_tensor(_decaying_density(mol, 1, beta=0.6), device='cuda')
+    opt = jk._VHFOpt(mol).build()
+    j1, k1 = jk.get_jk(mol, d1, hermi=1, vhfopt=opt)
+    j2, k2 = jk.get_jk(mol, d2, hermi=1, vhfopt=opt)
+    sj, sk = float(j1.abs().max()), float(k1.abs().max())
+    assert float((j1 - j1.T).abs().max()) < 1e-10 * sj and float((k1 - k1.T).abs().max()) < 1e-10 * sk
+    # linearity (screening is tighter than the tolerance: direct_scf_tol = 1e-13)
+    j12, k12 = jk.get_jk(mol, d1 + d2, hermi=1, vhfopt=opt)
+    assert float((j12 - j1 - j2).abs().max()) < 1e-9 * sj
+    assert float((k12 - k1 - k2).abs().max()) < 1e-9 * sk
+    # density exchange
+    t12, t21 = float((d1 * j2).sum()), float((d2 * j1).sum())
+    assert abs(t12 - t21) < 1e-10 * abs(t12)
+    t12, t21 = float((d1 * k2).sum()), float((d2 * k1).sum())
+    assert abs(t12 - t21) < 1e-10 * abs(t12)
+    # partition invariance
+    parts = []
+    for rank in range(2):
+        o = jk._VHFOpt(mol)
+        o.__dict__.update({k: v for k, v in opt.__dict__.items() if k not in ('rank', 'world')})
+        o.rank, o.world = rank, 2
+        dms = o.apply_coeff_C_mat_CT(d1.reshape(1, nao, nao)).contiguous()
+        # raw partial sums of this rank (no all_reduce: torch.distributed is not initialised)
+        parts.append(o.get_jk(dms, 1))
+    full = opt.get_jk(opt.apply_coeff_C_mat_CT(d1.reshape(1, nao, nao)).contiguous(), 1)
+    # get_jk symmetrises per call, and symmetrisation is linear
+    assert float((parts[0][0] + parts[1][0] - full[0]).abs().max()) < 1e-10 * sj
+    assert float((parts[0][1] + parts[1][1] - full[1]).abs().max()) < 1e-10 * sk
