@@ -190,6 +190,8 @@ def run_reference(args, rank):
     network); the restated CPU oracle is timed instead, on a bounded sample.'''
     if rank != 0:
         return
+    if 'TORCHELASTIC_RUN_ID' in os.environ or os.environ.get('OMP_NUM_THREADS') == '1':
+        os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)     # torchrun pins it to 1
     times = []
     cpu_oracle_sample(2, args.basis, args.mol)       # warm-up: loads the library, spins up OpenMP
     for _ in range(max(1, min(args.steps, 3))):

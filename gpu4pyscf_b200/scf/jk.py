@@ -8,12 +8,13 @@ Public surface kept from the reference (gpu4pyscf/scf/jk.py:60-230, 407-927):
 What is new underneath: host arrays are torch CUDA tensors (CuPy is not in the
 image; the C-ABI takes raw device pointers so it is array-library agnostic),
 the screening data are exactly q-sorted shell-pair lists per group pair, and one
-launch handles an unordered pair of group pairs {(gi,gj),(gk,gl)} -- the pair
-type with more Cartesian components is the register-tile side of the kernel
-(csrc/rys_jk_kernel.cuh).  Multi-GPU: one process per GPU; every rank takes the
-X pairs ``ix % world == rank`` of each q-sorted list (neighbours in the sorted
-order have near-equal cost, so the round-robin split is cost balanced) and the
-partial ``[vj|vk]`` buffers are summed with ONE ``all_reduce`` per build.
+launch handles an unordered pair of group pairs {(gi,gj),(gk,gl)} -- which of the
+two is the register-tile side of the kernel is the library's choice
+(B200_has_class).  Multi-GPU: one process per GPU; every rank takes the work
+items (X pair, chunk of the q-sorted Y list) with ``item % world == rank`` of each
+launch (neighbouring items have near-equal cost, so the round-robin deal is
+balanced) and the partial ``[vj|vk]`` buffers are summed with ONE ``all_reduce``
+per build.
 """
 import ctypes
 import math
