@@ -110,3 +110,27 @@ __host__ __device__ constexpr int cart_z(int l, int n)
 {
     return l - cart_x(l, n) - cart_y(l, n);
 }
+
+// N consecutive doubles of a density-matrix row: 16-byte loads when the caller has
+// checked that the row start is 16-byte aligned (even AO index, even nao)
+template <int N>
+__device__ __forceinline__ void ld_row(double (&dst)[N], const double *__restrict__ p, const bool vec)
+{
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i + 1 < N; i += 2) {
+#ifdef CPU_EMUL
+            dst[i] = p[i];
+            dst[i + 1] = p[i + 1];
+#else
+            const double2 v = __ldg((const double2 *)(p + i));
+            dst[i] = v.x;
+            dst[i + 1] = v.y;
+#endif
+        }
+        if (N & 1) dst[N - 1] = __ldg(p + N - 1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = __ldg(p + i);
+    }
+}

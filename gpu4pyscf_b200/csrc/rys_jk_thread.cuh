@@ -127,6 +127,9 @@ rys_jk_thread_kernel(JKTask t)
                 drs[i] = __ldg(t.dm + idm * nao2 + (size_t)(r0 + c) * nao + s0 + d);
             }
         }
+        // 16-byte loads of D rows when the r / s blocks start on an even AO index
+        const bool vec_r = NFR > 1 && ((r0 | nao) & 1) == 0;
+        const bool vec_s = NFS > 1 && ((s0 | nao) & 1) == 0;
         double jacc[NDM][NFRS];
 #pragma unroll
         for (int idm = 0; idm < NDM; ++idm)
@@ -367,10 +370,8 @@ rys_jk_thread_kernel(JKTask t)
                         double dqr[NFQ][NFR], dqs[NFQ][NFS];
 #pragma unroll
                         for (int b = 0; b < NFQ; ++b) {
-#pragma unroll
-                            for (int c = 0; c < NFR; ++c) dqr[b][c] = __ldg(dm + (size_t)(q0 + b) * nao + r0 + c);
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) dqs[b][d] = __ldg(dm + (size_t)(q0 + b) * nao + s0 + d);
+                            ld_row<NFR>(dqr[b], dm + (size_t)(q0 + b) * nao + r0, vec_r);
+                            ld_row<NFS>(dqs[b], dm + (size_t)(q0 + b) * nao + s0, vec_s);
                         }
 #pragma unroll
                         for (int a = 0; a < NFP; ++a) {
@@ -397,10 +398,8 @@ rys_jk_thread_kernel(JKTask t)
                         double dpr[NFP][NFR], dps[NFP][NFS];
 #pragma unroll
                         for (int a = 0; a < NFP; ++a) {
-#pragma unroll
-                            for (int c = 0; c < NFR; ++c) dpr[a][c] = __ldg(dm + (size_t)(p0 + a) * nao + r0 + c);
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) dps[a][d] = __ldg(dm + (size_t)(p0 + a) * nao + s0 + d);
+                            ld_row<NFR>(dpr[a], dm + (size_t)(p0 + a) * nao + r0, vec_r);
+                            ld_row<NFS>(dps[a], dm + (size_t)(p0 + a) * nao + s0, vec_s);
                         }
 #pragma unroll
                         for (int b = 0; b < NFQ; ++b) {

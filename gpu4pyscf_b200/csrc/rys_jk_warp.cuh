@@ -252,6 +252,8 @@ rys_jk_warp_kernel(JKTask t)
                 drs[i] = __ldg(t.dm + idm * nao2 + (size_t)(r0 + c) * nao + s0 + d);
             }
         }
+        const bool vec_r = NC > 1 && ((r0 | nao) & 1) == 0;
+        const bool vec_s = NFS > 1 && ((s0 | nao) & 1) == 0;
         double jacc[NDM][NC][NFS];
 #pragma unroll
         for (int idm = 0; idm < NDM; ++idm)
@@ -604,26 +606,36 @@ rys_jk_warp_kernel(JKTask t)
                         if (do_k) {
                             double *vk = t.vk + idm * nao2;
                             double dqs[NFS], dps[NFS], kps[NFS], kqs[NFS];
+                            ld_row<NFS>(dqs, dm + qrow + s0, vec_s);
+                            ld_row<NFS>(dps, dm + prow + s0, vec_s);
 #pragma unroll
                             for (int d = 0; d < NFS; ++d) {
-                                dqs[d] = __ldg(dm + qrow + s0 + d);
-                                dps[d] = __ldg(dm + prow + s0 + d);
                                 kps[d] = 0.;
                                 kqs[d] = 0.;
+                            }
+                            double dqr[NC], dpr[NC];
+                            if (NCS == 1) {
+                                ld_row<NC>(dqr, dm + qrow + r0, vec_r);
+                                ld_row<NC>(dpr, dm + prow + r0, vec_r);
+                            } else {
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) {
+                                    const int c = c0 + n < NFR ? c0 + n : NFR - 1;
+                                    dqr[n] = __ldg(dm + qrow + r0 + c);
+                                    dpr[n] = __ldg(dm + prow + r0 + c);
+                                }
                             }
 #pragma unroll
                             for (int n = 0; n < NC; ++n) {
                                 if (c0 + n < NFR) {
-                                    double dqr = __ldg(dm + qrow + r0 + c0 + n);
-                                    double dpr = __ldg(dm + prow + r0 + c0 + n);
                                     double kpr = 0., kqr = 0.;
 #pragma unroll
                                     for (int d = 0; d < NFS; ++d) {
                                         double gv = gout[n][d];
                                         kpr += gv * dqs[d];
                                         kqr += gv * dps[d];
-                                        kps[d] += gv * dqr;
-                                        kqs[d] += gv * dpr;
+                                        kps[d] += gv * dqr[n];
+                                        kqs[d] += gv * dpr[n];
                                     }
                                     JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr);
                                     JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr);

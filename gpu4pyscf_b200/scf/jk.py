@@ -18,6 +18,7 @@ per build.
 """
 import ctypes
 import math
+import os
 import numpy as np
 import torch
 
@@ -99,6 +100,8 @@ class _VHFOpt:
         # reference's _TimingCollector (jk.py:1170-1188); costs a sync per class
         self.class_timing = None
         self.n_streams = 4
+        # width (log units) of the q bins of the pair lists; 0 = exactly q-sorted lists
+        self.q_bin = float(os.environ.get('B200_Q_BIN', '0.5'))
         self._streams = None
 
     def reset(self, mol):
@@ -125,7 +128,7 @@ class _VHFOpt:
                 'implementation has no CPU fallback')
         self._make_rys_envs()
         self.bas_pair_cache = _cache_q_cond_and_non0pairs(
-            smol, self._rys_envs, self.direct_scf_tol, self.device, lib)
+            smol, self._rys_envs, self.direct_scf_tol, self.device, lib, self.q_bin)
         return self
 
     def _make_rys_envs(self):
@@ -266,7 +269,7 @@ class _VHFOpt:
             err = lib.B200_build_jk_class(
                 _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
                 _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
-                _ptr(dm_cond), cutoff, dm_penalty, 0., dedupe, rank, world, head, stream, _ptr(rec_y))
+                _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, rank, world, head, stream, _ptr(rec_y))
             if err:
                 raise RuntimeError('B200_build_jk_class failed for class %s' % (tuple(lprim),))
             if self.class_timing is not None and dev.type == 'cuda':
@@ -325,12 +328,12 @@ class _VHFOpt:
     @property
     def _qmax(self):
         if getattr(self, '_qmax_cache', None) is None:
-            self._qmax_cache = {k: (float(v[1][0]) if len(v[1]) else -1e30)
+            self._qmax_cache = {k: (float(v[1].max()) if len(v[1]) else -1e30)
                                 for k, v in self.bas_pair_cache.items()}
         return self._qmax_cache
 
 
-def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib):
+def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib, q_bin=0.):
     '''Per group pair (gi >= gj): shell-pair ids ``ish*nbas+jsh`` (ish >= jsh),
     their Schwarz bounds q = 1/2 log max|(ij|ij)| and the same again as
     ``s_cond`` -- each list sorted by q descending (exactly; the reference bins
@@ -365,7 +368,14 @@ def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib):
     for key, (ids, q) in raw.items():
         keep = q + qmax > log_cutoff
         ids, q = ids[keep], q[keep]
-        order = torch.argsort(q, descending=True, stable=True)
+        if q_bin > 0:
+            # descending q bins of width q_bin, shell-pair order (ish, jsh) inside a bin:
+            # neighbours in the list share the bra shell, so the D rows they load and the
+            # K rows they update coincide (the kernels get q_margin = q_bin for the early exit)
+            bins = torch.floor(q.double() / q_bin).to(torch.int64)
+            order = torch.argsort((bins.max() - bins) * (int(nbas) * int(nbas)) + ids.to(torch.int64))
+        else:
+            order = torch.argsort(q, descending=True, stable=True)
         ids = ids[order].contiguous()
         q = q[order].contiguous()
         # Gaussian-product records of the pairs, in list order
