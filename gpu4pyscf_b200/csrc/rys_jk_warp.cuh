@@ -576,43 +576,66 @@ rys_jk_warp_kernel(JKTask t)
                 }
             };
             // J/K digestion of quartet slot j with this lane's tile (reference: rys_contract_jk.cu:304-329)
+            // Within a single-warp team the lanes (a, b) of one quartet hold partial sums of the
+            // same K rows: K_p* over b, K_q* over a.  They are combined with segmented
+            // shuffle reductions so that one lane per row issues the atomic.
+            constexpr bool SHFL_RED = (TW == 1);
+            auto red_b = [&](double v) {          // sum over b (lane stride NCS), result in the b == 0 lane
+#pragma unroll
+                for (int off = 1; off < NFQ; off <<= 1) {
+                    const double tv = __shfl_down_sync(0xffffffffu, v, off * NCS);
+                    if (b + off < NFQ) v += tv;
+                }
+                return v;
+            };
+            auto red_a = [&](double v) {          // sum over a (lane stride NFQ*NCS), result in the a == 0 lane
+#pragma unroll
+                for (int off = 1; off < C::NFP; off <<= 1) {
+                    const double tv = __shfl_down_sync(0xffffffffu, v, off * NFQ * NCS);
+                    if (a + off < C::NFP) v += tv;
+                }
+                return v;
+            };
             auto digest = [&](double (&gout)[NC][NFS], const int j) {
-                if (lane_on && j < nb) {
-                    const double *sl = slots + j * slot_d;
-                    const int *pi = (const int *)(sl + 7);
-                    const int p0 = pi[0];
-                    const int q0 = pi[1];
-                    const size_t prow = (size_t)(p0 + a) * nao;
-                    const size_t qrow = (size_t)(q0 + b) * nao;
+                const bool on = lane_on && j < nb;
+                int p0 = 0, q0 = 0;
+                if (on) {
+                    const int *pi = (const int *)(slots + j * slot_d + 7);
+                    p0 = pi[0];
+                    q0 = pi[1];
+                }
+                const size_t prow = (size_t)(p0 + a) * nao;
+                const size_t qrow = (size_t)(q0 + b) * nao;
 #pragma unroll
-                    for (int idm = 0; idm < NDM; ++idm) {
-                        const double *dm = t.dm + idm * nao2;
-                        if (do_j) {
-                            double *vj = t.vj + idm * nao2;
-                            double dpq = __ldg(dm + prow + q0 + b);
-                            double s = 0.;
+                for (int idm = 0; idm < NDM; ++idm) {
+                    const double *dm = t.dm + idm * nao2;
+                    if (do_j && on) {
+                        double *vj = t.vj + idm * nao2;
+                        double dpq = __ldg(dm + prow + q0 + b);
+                        double s = 0.;
 #pragma unroll
-                            for (int n = 0; n < NC; ++n) {
-                                if (c0 + n < NFR) {
+                        for (int n = 0; n < NC; ++n) {
+                            if (c0 + n < NFR) {
 #pragma unroll
-                                    for (int d = 0; d < NFS; ++d) {
-                                        s += gout[n][d] * drs[idm * NFRS + (c0 + n) * NFS + d];
-                                        jacc[idm][n][d] += gout[n][d] * dpq;
-                                    }
+                                for (int d = 0; d < NFS; ++d) {
+                                    s += gout[n][d] * drs[idm * NFRS + (c0 + n) * NFS + d];
+                                    jacc[idm][n][d] += gout[n][d] * dpq;
                                 }
                             }
-                            JK_ATOMIC_ADD(vj + prow + q0 + b, s);
                         }
-                        if (do_k) {
-                            double *vk = t.vk + idm * nao2;
-                            double dqs[NFS], dps[NFS], kps[NFS], kqs[NFS];
+                        JK_ATOMIC_ADD(vj + prow + q0 + b, s);
+                    }
+                    if (do_k) {
+                        double *vk = t.vk + idm * nao2;
+                        double kpr[NC], kqr[NC], kps[NFS], kqs[NFS];
+#pragma unroll
+                        for (int n = 0; n < NC; ++n) kpr[n] = kqr[n] = 0.;
+#pragma unroll
+                        for (int d = 0; d < NFS; ++d) kps[d] = kqs[d] = 0.;
+                        if (on) {
+                            double dqs[NFS], dps[NFS];
                             ld_row<NFS>(dqs, dm + qrow + s0, vec_s);
                             ld_row<NFS>(dps, dm + prow + s0, vec_s);
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) {
-                                kps[d] = 0.;
-                                kqs[d] = 0.;
-                            }
                             double dqr[NC], dpr[NC];
                             if (NCS == 1) {
                                 ld_row<NC>(dqr, dm + qrow + r0, vec_r);
@@ -628,23 +651,46 @@ rys_jk_warp_kernel(JKTask t)
 #pragma unroll
                             for (int n = 0; n < NC; ++n) {
                                 if (c0 + n < NFR) {
-                                    double kpr = 0., kqr = 0.;
 #pragma unroll
                                     for (int d = 0; d < NFS; ++d) {
-                                        double gv = gout[n][d];
-                                        kpr += gv * dqs[d];
-                                        kqr += gv * dps[d];
+                                        const double gv = gout[n][d];
+                                        kpr[n] += gv * dqs[d];
+                                        kqr[n] += gv * dps[d];
                                         kps[d] += gv * dqr[n];
                                         kqs[d] += gv * dpr[n];
                                     }
-                                    JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr);
-                                    JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr);
+                                }
+                            }
+                        }
+                        bool lead_p = true, lead_q = true;      // does this lane issue the p-row / q-row atomics
+                        if (SHFL_RED) {
+                            if (NFQ > 1) {
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) kpr[n] = red_b(kpr[n]);
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) kps[d] = red_b(kps[d]);
+                                lead_p = b == 0;
+                            }
+                            if (C::NFP > 1) {
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) kqr[n] = red_a(kqr[n]);
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) kqs[d] = red_a(kqs[d]);
+                                lead_q = a == 0;
+                            }
+                        }
+                        if (on) {
+#pragma unroll
+                            for (int n = 0; n < NC; ++n) {
+                                if (c0 + n < NFR) {
+                                    if (lead_p) JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr[n]);
+                                    if (lead_q) JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr[n]);
                                 }
                             }
 #pragma unroll
                             for (int d = 0; d < NFS; ++d) {
-                                JK_ATOMIC_ADD(vk + prow + s0 + d, kps[d]);
-                                JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
+                                if (lead_p) JK_ATOMIC_ADD(vk + prow + s0 + d, kps[d]);
+                                if (lead_q) JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
                             }
                         }
                     }
