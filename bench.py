@@ -346,7 +346,12 @@ def main():
             'tflops_fp64': achieved,
             'f_alg': f_alg_total,
             'roofline': {'bound': 'fp64_fma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / (peak * world) if peak else None, 'traffic': None,
+                         'frac': achieved / (peak * world) if peak else None,
+                         # DRAM bytes of ALL class launches of one build (ncu dram__bytes_read+write summed over the
+                         # 667 launches, profiles/launches_r1_summary.txt); not re-measured live.  Mostly local-memory
+                         # spill traffic of the thread-per-quartet kernels; D, J, K themselves are 155 MB.
+                         'traffic': 79.8e9 if (args.mol, args.basis.lower()) in F_ALG_FULL and world == 1 else None,
+                         'traffic_unit': 'bytes per build, all launches',
                          'peak_source': 'DFMA burn measured in this run on rank 0 (MEASURED_PEAKS.json has no FP64 figure)',
                          'kernel': 'rys_jk_kernel / rys_jk_thread_kernel class family (%d launches, %.1f ms of the %.1f ms step on rank 0)'
                                    % (nlaunch, kern_ms, ms_step),

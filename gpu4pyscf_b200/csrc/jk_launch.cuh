@@ -104,7 +104,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         fprintf(stderr, "rys_jk: more than %d primitive pairs per shell pair\n", JK_MAXPP);
         return 1;
     }
-    int nteams = JKW_MAXTHREADS / C::TEAM;
+    int nteams = jkw_block_threads(C::TEAM) / C::TEAM;
     const int nprimq = npq * nrs;
     // g-sets per lane slot: fill (not overfill) the team in the recurrence phase,
     // whose work items are (g-set, root, axis)

@@ -103,19 +103,27 @@ __device__ __forceinline__ void jkw_st_seg(double *p, const double (&src)[N])
 #define JKW_MAXTHREADS 256
 #endif
 // resident blocks per SM asked from the register allocator, by register-tile size
+__host__ __device__ constexpr int jkw_block_threads(int team)
+{
+    return team > JKW_MAXTHREADS ? team : (JKW_MAXTHREADS / team) * team;
+}
+#ifndef JKW_MID_WARPS
+#define JKW_MID_WARPS 16     // resident warps per SM asked for mid-size register tiles (16 -> 128 registers)
+#endif
 __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int team)
 {
-    // doubles that stay live across the whole Y stream: gout + J_rs accumulators
+    // doubles that stay live across the whole work item: gout + J_rs accumulators
     int d = tile * (1 + ndm);
-    int threads = (JKW_MAXTHREADS / team) * team;
-    int nb = d <= 24 ? 3 : (d <= 44 ? 2 : 1);      // 256 threads: 85 / 128 / 255 registers
+    int threads = jkw_block_threads(team);
+    int warps = d <= 24 ? 24 : (d <= 44 ? JKW_MID_WARPS : 8);      // 85 / 128 / 255 registers
     (void)sub;
-    return threads <= 128 ? 2 * nb : nb;
+    int nb = warps * 32 / threads;
+    return nb < 1 ? 1 : nb;
 }
 
 template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
 __global__ void
-__launch_bounds__((JKW_MAXTHREADS / JKWCfg<LP, LQ, LR, LS, NCS>::TEAM) * JKWCfg<LP, LQ, LR, LS, NCS>::TEAM,
+__launch_bounds__(jkw_block_threads(JKWCfg<LP, LQ, LR, LS, NCS>::TEAM),
                   jkw_minblocks(JKWCfg<LP, LQ, LR, LS, NCS>::TILE, NDM,
                                 NCS == 1 ? JKWCfg<LP, LQ, LR, LS, NCS>::SUBSIZE : LS + 1,
                                 JKWCfg<LP, LQ, LR, LS, NCS>::TEAM))
