@@ -341,7 +341,7 @@ def main():
                                    % (args.mol, args.basis),
                        'nao': nao, 'nao_sorted_cart': nao_s, 'nbas_sorted': opt.sorted_mol.nbas,
                        'density': 'synthetic symmetric, exp(-0.8 R_AB/Bohr) decay + identity (no SCF driver in scope)',
-                       'parallelism': 'q-sorted shell-pair lists dealt round-robin over %d rank(s), one all-reduce of [J|K]' % world,
+                       'parallelism': '(X pair, Y chunk) work items of every class launch dealt round-robin over %d rank(s), one all-reduce of [J|K]' % world,
                        'l2': 'inputs+outputs (D,J,K = %.0f MB) exceed L2; kernels are FP64-compute bound' % (3 * nao_s * nao_s * 8 / 1e6)},
             'tflops_fp64': achieved,
             'f_alg': f_alg_total,

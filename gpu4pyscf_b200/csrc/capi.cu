@@ -94,7 +94,8 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const uint32_t *pair_x, const float *q_x, int npair_x,
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
-                        int dedupe, int rank, int world, int *head, void *stream, const double *rec_y)
+                        int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
+                        double omega)
 {
     if (npair_x <= 0 || npair_y <= 0) return 0;
     if (RYS_b200_init()) return 1;
@@ -121,6 +122,11 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
     t.dedupe = dedupe;
     t.head = head;
     t.rec_y = rec_y;
+    if (omega < 0.) {
+        fprintf(stderr, "B200_build_jk_class: omega < 0 (short range) is composed on the host as full - long range\n");
+        return 1;
+    }
+    t.omega = omega;
     t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
     t.rank = rank;
     t.world = world < 1 ? 1 : world;
@@ -184,13 +190,13 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
         return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
                                    pair_kl_mapping, q_cond_kl, npairs_kl,
                                    pair_ij_mapping, q_cond_ij, npairs_ij,
-                                   dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr, nullptr);
+                                   dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr, nullptr, env[8]);
     } else {
         int lprim[8] = {lk, ll, li, lj, nk, nl, ni, nj};
         return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
                                    pair_ij_mapping, q_cond_ij, npairs_ij,
                                    pair_kl_mapping, q_cond_kl, npairs_kl,
-                                   dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr, nullptr);
+                                   dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr, nullptr, env[8]);
     }
 }
 

@@ -309,12 +309,18 @@ rys_jk_kernel(JKTask t)
                         double zeta = pp[0], eta = rr[0];
                         double dx = pp[1] - rr[1], dy = pp[2] - rr[2], dz = pp[3] - rr[3];
                         double ze = zeta + eta;
-                        double x = zeta * eta / ze * (dx * dx + dy * dy + dz * dz);
+                        double theta = zeta * eta / ze;
+                        double x = theta * (dx * dx + dy * dy + dz * dz);
+                        double lrf = 1.;                       // long-range attenuation: theta -> theta * lrf
+                        if (t.omega != 0.) {
+                            lrf = t.omega * t.omega / (t.omega * t.omega + theta);
+                            x *= lrf;
+                        }
                         double v = rys_value<NROOTS>(idx, x, t.rys_cheb, t.rys_large);
                         if (idx < NROOTS) {
-                            sl_rw[idx] = v / ze;
+                            sl_rw[idx] = v * lrf / ze;
                         } else {
-                            sl_rw[idx] = v * (sl[SLOT_FAC] * pp[4] * rr[4] / (zeta * eta * sqrt(ze)));
+                            sl_rw[idx] = v * sqrt(lrf) * (sl[SLOT_FAC] * pp[4] * rr[4] / (zeta * eta * sqrt(ze)));
                         }
                     }
                     __syncthreads();

@@ -247,12 +247,20 @@ rys_jk_thread_kernel(JKTask t)
                         const double PQx = Px - rr[1], PQy = Py - rr[2], PQz = Pz - rr[3];
                         const double ze = zeta + eta;
                         const double zei = 1. / ze;
-                        const double x = zeta * eta * zei * (PQx * PQx + PQy * PQy + PQz * PQz);
-                        const double pref = cpq * rr[4] / (zeta * eta * sqrt(ze));
+                        const double theta = zeta * eta * zei;
+                        double x = theta * (PQx * PQx + PQy * PQy + PQz * PQz);
+                        double pref = cpq * rr[4] / (zeta * eta * sqrt(ze));
+                        double rscale = zei;
+                        if (t.omega != 0.) {                   // long-range erf(omega r)/r: theta -> theta * lrf
+                            const double lrf = t.omega * t.omega / (t.omega * t.omega + theta);
+                            x *= lrf;
+                            rscale *= lrf;
+                            pref *= sqrt(lrf);
+                        }
                         const double hz = .5 / zeta, he = .5 / eta;
 #pragma unroll
                         for (int root = 0; root < NROOTS; ++root) {
-                            const double rt_aa = rys_value_s<NROOTS>(root, x, rys_tab) * zei;
+                            const double rt_aa = rys_value_s<NROOTS>(root, x, rys_tab) * rscale;
                             const double wt = rys_value_s<NROOTS>(NROOTS + root, x, rys_tab) * pref;
                             const double rt_aij = rt_aa * eta;
                             const double rt_akl = rt_aa * zeta;

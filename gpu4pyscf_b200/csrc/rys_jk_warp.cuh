@@ -412,14 +412,20 @@ rys_jk_warp_kernel(JKTask t)
                     double zeta = pp[0], eta = rr[0];
                     double dx = pp[1] - rr[1], dy = pp[2] - rr[2], dz = pp[3] - rr[3];
                     double ze = zeta + eta;
-                    double x = zeta * eta / ze * (dx * dx + dy * dy + dz * dz);
+                    double theta = zeta * eta / ze;
+                    double x = theta * (dx * dx + dy * dy + dz * dz);
+                    double lrf = 1.;                           // long-range attenuation: theta -> theta * lrf
+                    if (t.omega != 0.) {
+                        lrf = t.omega * t.omega / (t.omega * t.omega + theta);
+                        x *= lrf;
+                    }
                     double v = rys_value_s<NROOTS>(idx, x, rys_tab);
                     double *rw = gsets + g * GSET;
                     if (idx < NROOTS) {
-                        rw[idx] = v / ze;
+                        rw[idx] = v * lrf / ze;
                     } else {
                         double w = valid ? sl[6] * pp[4] * rr[4] / (zeta * eta * sqrt(ze)) : 0.;
-                        rw[idx] = v * w;
+                        rw[idx] = v * w * sqrt(lrf);
                     }
                 }
                 jkw_team_sync<TW>(team);

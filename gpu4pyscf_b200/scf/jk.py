@@ -52,17 +52,37 @@ def get_jk(mol, dm, hermi=0, vhfopt=None, with_j=True, with_k=True,
         vhfopt = _VHFOpt(mol).build()
     if omega is None:
         omega = mol.omega
-    if omega != 0 or lr_factor is not None or sr_factor is not None:
-        raise NotImplementedError('range-separated J/K (omega != 0) is a "next" row of the scope table')
     dm = _as_device_tensor(dm, vhfopt.device)
     nao_orig = dm.shape[-1]
     dms = dm.reshape(-1, nao_orig, nao_orig)
     dms = vhfopt.apply_coeff_C_mat_CT(dms).contiguous()
-    vj, vk = vhfopt.get_jk(dms, hermi, verbose, with_j=with_j, with_k=with_k)
+    # Range separation (reference: jk.py:1122-1168).  The kernels evaluate the full
+    # operator (omega = 0) or the long-range one erf(|omega| r)/r; everything else is
+    # a linear combination:  SR = full - LR,  lr_factor*LR + sr_factor*SR =
+    # sr_factor*full + (lr_factor - sr_factor)*LR.
+    if omega == 0 or omega is None:
+        c_full, c_lr = 1., 0.
+        if lr_factor is not None or sr_factor is not None:
+            raise ValueError('lr_factor/sr_factor need omega != 0')
+    elif lr_factor is None and sr_factor is None:
+        c_full, c_lr = (0., 1.) if omega > 0 else (1., -1.)
+    else:
+        lr = 0. if lr_factor is None else float(lr_factor)
+        sr = 0. if sr_factor is None else float(sr_factor)
+        c_full, c_lr = sr, lr - sr
+    vj = vk = None
+    for coef, w in ((c_full, 0.), (c_lr, abs(float(omega or 0.)))):
+        if coef == 0:
+            continue
+        tj, tk = vhfopt.get_jk(dms, hermi, verbose, with_j=with_j, with_k=with_k, omega=w)
+        if tj is not None:
+            vj = coef * tj if vj is None else vj + coef * tj
+        if tk is not None:
+            vk = coef * tk if vk is None else vk + coef * tk
     if with_k:
-        vk = vhfopt.apply_coeff_CT_mat_C(vk).reshape(dm.shape)
+        vk = vhfopt.apply_coeff_CT_mat_C(vk).reshape(dm.shape) if vk is not None else torch.zeros_like(dm)
     if with_j:
-        if vj is None:      # hermi == 2: J of an anti-symmetric density vanishes
+        if vj is None:      # hermi == 2 (J of an anti-symmetric density vanishes) or zero coefficients
             vj = torch.zeros_like(dm)
         else:
             vj = vhfopt.apply_coeff_CT_mat_C(vj).reshape(dm.shape)
@@ -189,9 +209,12 @@ class _VHFOpt:
         self._tasks = tasks
         return tasks
 
-    def get_jk(self, dms, hermi=0, verbose=None, with_j=True, with_k=True):
+    def get_jk(self, dms, hermi=0, verbose=None, with_j=True, with_k=True, omega=0.):
         '''J/K in the sorted Cartesian basis.  dms: (n_dm, nao, nao) device
-        tensor.  Returns (vj, vk) (None where not requested).'''
+        tensor.  Returns (vj, vk) (None where not requested).  omega = 0: 1/r,
+        omega > 0: long-range erf(omega r)/r.'''
+        if omega < 0:
+            raise ValueError('short range is composed by the caller as full - long range')
         lib = loader.load_library()
         smol = self.sorted_mol
         dev = self.device
@@ -269,7 +292,7 @@ class _VHFOpt:
             err = lib.B200_build_jk_class(
                 _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
                 _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
-                _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, rank, world, head, stream, _ptr(rec_y))
+                _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, rank, world, head, stream, _ptr(rec_y), float(omega))
             if err:
                 raise RuntimeError('B200_build_jk_class failed for class %s' % (tuple(lprim),))
             if self.class_timing is not None and dev.type == 'cuda':
@@ -321,9 +344,21 @@ class _VHFOpt:
         return self.get_jk(dms, 1, verbose, with_j=True, with_k=False)[0]
 
     def get_k(self, dms, hermi=0, verbose=None, omega=0, lr_factor=None, sr_factor=None):
-        if omega:
-            raise NotImplementedError('range-separated K')
-        return self.get_jk(dms, hermi, verbose, with_j=False, with_k=True)[1]
+        if not omega:
+            return self.get_jk(dms, hermi, verbose, with_j=False, with_k=True)[1]
+        if lr_factor is None and sr_factor is None:
+            c_full, c_lr = (0., 1.) if omega > 0 else (1., -1.)
+        else:
+            lr = 0. if lr_factor is None else float(lr_factor)
+            sr = 0. if sr_factor is None else float(sr_factor)
+            c_full, c_lr = sr, lr - sr
+        vk = None
+        for coef, w in ((c_full, 0.), (c_lr, abs(float(omega)))):
+            if coef == 0:
+                continue
+            tk = self.get_jk(dms, hermi, verbose, with_j=False, with_k=True, omega=w)[1]
+            vk = coef * tk if vk is None else vk + coef * tk
+        return vk
 
     @property
     def _qmax(self):

@@ -52,8 +52,9 @@ int cuda_version(void);
  * pair_ij >= pair_kl (pair id = ish*nbas+jsh); vj/vk receive the partial
  * (un-symmetrised) sums of jk.py:594-616.  pool must hold at least one int;
  * bas and env are HOST copies (only bas is read, for l and nprim).
- * s_cond_*, diffuse_exps and shm_size are accepted for signature
- * compatibility and ignored (omega == 0 path). */
+ * env[8] = omega (HOST): 0 or > 0 (long range); omega < 0 returns an error (the
+ * caller composes short range as full - long range).  s_cond_*, diffuse_exps
+ * and shm_size are accepted for signature compatibility and ignored. */
 int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
                  RysIntEnvVars *envs, int *shls_slice, int shm_size,
                  int npairs_ij, int npairs_kl,
@@ -74,13 +75,17 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
  *   partition of the q-sorted list); head: zeroed device int work counter.
  *   rec_y: optional per-pair records of the Y list (B200_pair_records), NULL to
  *   derive the Gaussian products from bas/env inside the kernel.
+ *   omega: 0 for 1/r, > 0 for the long-range operator erf(omega r)/r (reference:
+ *   rys_roots_rs, lib/gvhf-rys/rys_roots.cu:91-119); the short-range operator is
+ *   composed on the host as full - long range, so omega < 0 is rejected here.
  * vj or vk may be NULL (K-only / J-only).  n_dm is arbitrary. */
 int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
                         const RysIntEnvVars *envs, const int *lprim,
                         const uint32_t *pair_x, const float *q_x, int npair_x,
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
-                        int dedupe, int rank, int world, int *head, void *stream, const double *rec_y);
+                        int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
+                        double omega);
 
 /* 1 if a kernel is instantiated with (lp,lq) as the lane side (Y) and (lr,ls)
  * as the register-tile side (X); exactly one orientation of every unordered

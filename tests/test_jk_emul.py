@@ -33,8 +33,9 @@ if hermi == 1:
     dm = dm + dm.transpose(0, 2, 1)
 elif hermi == 2:
     dm = dm - dm.transpose(0, 2, 1)
-vj, vk = jk.get_jk(mol, dm, hermi=hermi)
-rj, rk = oracle.get_jk(mol, dm, hermi=0)
+omega = float(os.environ.get('TEST_OMEGA', '0'))
+vj, vk = jk.get_jk(mol, dm, hermi=hermi, omega=omega)
+rj, rk = oracle.get_jk(mol, dm, hermi=0, omega=omega)
 if hermi != 2:
     assert abs(vj.numpy() - rj).max() < 1e-10, abs(vj.numpy() - rj).max()
 assert abs(vk.numpy() - rk).max() < 1e-10, abs(vk.numpy() - rk).max()
@@ -42,9 +43,12 @@ print('OK')
 ''' % ROOT
 
 
-@pytest.mark.parametrize('case,hermi,ychunk', [('sto', 1, 0), ('sto', 0, 3), ('sto', 2, 0), ('2', 1, 7), ('3', 0, 0), ('tz', 1, 5)])
+@pytest.mark.parametrize('case,hermi,ychunk', [('sto', 1, 0), ('sto', 0, 3), ('sto', 2, 0), ('2', 1, 7), ('3', 0, 0), ('tz', 1, 5), ('rs', 1, 0)])
 def test_emulated_kernels_match_oracle(case, hermi, ychunk):
     env = dict(os.environ)
+    if case == 'rs':
+        case = 'tz'
+        env['TEST_OMEGA'] = '-0.35'             # short range = full - long range (two builds)
     if ychunk:
         env['B200_YCHUNK'] = str(ychunk)      # tiny Y chunks: many (X pair, Y chunk) work items
     r = subprocess.run([sys.executable, '-c', SCRIPT, case, str(hermi)], env=env,

@@ -256,3 +256,33 @@ def test_full_size_properties():
     # get_jk symmetrises per call, and symmetrisation is linear
     assert float((parts[0][0] + parts[1][0] - full[0]).abs().max()) < 1e-10 * sj
     assert float((parts[0][1] + parts[1][1] - full[1]).abs().max()) < 1e-10 * sk
+
+
+@pytest.mark.parametrize('omega', [0.3, -0.3])
+def test_range_separated(omega):
+    """omega > 0: long-range erf(omega r)/r; omega < 0: short-range erfc(|omega| r)/r
+    (libcint sign convention; reference gpu4pyscf/scf/jk.py:1122-1168, tests
+    test_scf_jk.py:358-386)."""
+    from gpu4pyscf_b200.scf import jk
+    oracle = _oracle()
+    mol = molecules.water('def2-tzvp')
+    np.random.seed(11)
+    dm = np.random.rand(mol.nao, mol.nao)
+    dm = dm + dm.T
+    vj, vk = jk.get_jk(mol, dm, hermi=1, omega=omega)
+    rj, rk = oracle.get_jk(mol, dm, hermi=1, omega=omega)
+    assert abs(vj.cpu().numpy() - rj).max() < 1e-10 * max(1., abs(rj).max())
+    assert abs(vk.cpu().numpy() - rk).max() < 1e-10 * max(1., abs(rk).max())
+
+
+def test_range_separated_k_factors():
+    from gpu4pyscf_b200.scf import jk
+    oracle = _oracle()
+    mol = molecules.mol1_lmax(3)
+    np.random.seed(12)
+    dm = np.random.rand(mol.nao, mol.nao)
+    dm = dm + dm.T
+    vk = jk.get_k(mol, dm, hermi=1, omega=0.4, lr_factor=0.65, sr_factor=0.2)
+    rk = (0.65 * oracle.get_jk(mol, dm, hermi=1, omega=0.4)[1]
+          + 0.2 * oracle.get_jk(mol, dm, hermi=1, omega=-0.4)[1])
+    assert abs(vk.cpu().numpy() - rk).max() < 1e-10 * max(1., abs(rk).max())
