@@ -93,10 +93,10 @@ int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
 }
 
 // warp-team kernel (mid and high classes)
-template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
+template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0>
 int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
 {
-    typedef JKWCfg<LP, LQ, LR, LS, NCS> C;
+    typedef JKWCfg<LP, LQ, LR, LS, NCS, BL> C;
     static_assert(C::TW <= 8, "team larger than a 256-thread block");
     int npq = t->nprim_p * t->nprim_q;
     int nrs = t->nprim_r * t->nprim_s;
@@ -106,6 +106,10 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     }
     int nteams = jkw_block_threads(C::TEAM) / C::TEAM;
     const int nprimq = npq * nrs;
+    if (BL && nprimq != 1) {
+        fprintf(stderr, "rys_jk_warp: the b-loop variant only handles uncontracted launches\n");
+        return 1;
+    }
     // g-sets per lane slot: fill (not overfill) the team in the recurrence phase,
     // whose work items are (g-set, root, axis)
     int K = C::TEAM / (C::NSW * 3 * C::NROOTS);
@@ -128,7 +132,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     }
     t->nq = K;
     t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET);
-    int per_sm = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM>, smem, nt);
+    int per_sm = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL>, smem, nt);
     if (per_sm < 1) {
         fprintf(stderr, "rys_jk_warp: class (%d%d|%d%d) cannot be made resident (smem %d, threads %d)\n",
                 LP, LQ, LR, LS, smem, nt);
@@ -138,6 +142,6 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     int nitems = jk_set_chunks(t, grid * nteams);
     if (grid * nteams > nitems) grid = (nitems + nteams - 1) / nteams;
     if (grid < 1) return 0;
-    KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM>), grid, nt, smem, stream, *t);
+    KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_warp_kernel");
 }

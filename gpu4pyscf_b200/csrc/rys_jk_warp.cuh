@@ -27,12 +27,17 @@
 #include "rys_roots.cuh"
 #include "rys_jk_kernel.cuh"
 
-template <int LP, int LQ, int LR, int LS, int NCS>
+// BL = 1 ("b loop", uncontracted launches only): a lane owns a Cartesian component a of
+// shell p and loops over the nf_q components b itself, so a quartet needs nf_p*NCS lanes
+// instead of nf_p*nf_q*NCS and a warp carries nf_q times more quartets.
+template <int LP, int LQ, int LR, int LS, int NCS, int BL = 0>
 struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
     typedef JKCfg<LP, LQ, LR, LS, NCS> B;
-    static constexpr int TW = (B::G + 31) / 32;          // warps per team
+    static constexpr int G = (BL ? B::NFP : B::NFPQ) * NCS;   // lanes per quartet
+    static constexpr int NBL = BL ? B::NFQ : 1;               // b components per lane
+    static constexpr int TW = (G + 31) / 32;             // warps per team
     static constexpr int TEAM = TW * 32;
-    static constexpr int NSW = TW == 1 ? 32 / B::G : 1;  // quartets per team in the contraction phase
+    static constexpr int NSW = TW == 1 ? 32 / G : 1;     // quartets per team in the contraction phase
     // strides (in doubles) are even with an odd half: segments are 16-byte aligned
     // for 128-bit shared-memory accesses and consecutive segments / (root,axis)
     // blocks / g-sets start in different 16-byte bank groups
@@ -121,15 +126,16 @@ __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int 
     return nb < 1 ? 1 : nb;
 }
 
-template <int LP, int LQ, int LR, int LS, int NCS, int NDM>
+template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0>
 __global__ void
-__launch_bounds__(jkw_block_threads(JKWCfg<LP, LQ, LR, LS, NCS>::TEAM),
-                  jkw_minblocks(JKWCfg<LP, LQ, LR, LS, NCS>::TILE, NDM,
-                                NCS == 1 ? JKWCfg<LP, LQ, LR, LS, NCS>::SUBSIZE : LS + 1,
-                                JKWCfg<LP, LQ, LR, LS, NCS>::TEAM))
+__launch_bounds__(jkw_block_threads(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM),
+                  jkw_minblocks(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE, NDM,
+                                NCS == 1 ? JKWCfg<LP, LQ, LR, LS, NCS, BL>::SUBSIZE : LS + 1,
+                                JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM))
 rys_jk_warp_kernel(JKTask t)
 {
-    typedef JKWCfg<LP, LQ, LR, LS, NCS> C;
+    typedef JKWCfg<LP, LQ, LR, LS, NCS, BL> C;
+    constexpr int NBL = C::NBL;
     constexpr int NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS, NFRS = C::NFRS;
     constexpr int LPQ = C::LPQ, LRS = C::LRS, NROOTS = C::NROOTS;
     constexpr int NC = C::NC, G = C::G;
@@ -183,14 +189,13 @@ rys_jk_warp_kernel(JKTask t)
     const int s4 = (TW == 1) ? lane / G : 0;
     const bool lane_on = (TW == 1) ? (s4 < NSW) : (lt < G);
     const int tg = lane_on ? ((TW == 1) ? lane - s4 * G : lt) : 0;
-    const int ab = tg / NCS;
+    const int ab = tg / NCS;                      // BL: ab is the p component a itself
     const int cpart = tg - ab * NCS;
-    const int a = ab / NFQ;
-    const int b = ab - a * NFQ;
+    const int a = BL ? ab : ab / NFQ;
+    const int b = BL ? 0 : ab - a * NFQ;          // BL: b is a loop index, not a lane property
     const int c0 = cpart * NC;
-    const int gbx = (cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * SUBP;
-    const int gby = (cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * SUBP + GSIZEP;
-    const int gbz = (cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * SUBP + 2 * GSIZEP;
+    const int eax = cart_x(LP, a) * (LQ + 1), eay = cart_y(LP, a) * (LQ + 1), eaz = cart_z(LP, a) * (LQ + 1);
+    const int ebx0 = cart_x(LQ, b), eby0 = cart_y(LQ, b), ebz0 = cart_z(LQ, b);
     int ox[NC], oy[NC], oz[NC];
 #pragma unroll
     for (int n = 0; n < NC; ++n) {
@@ -520,8 +525,12 @@ rys_jk_warp_kernel(JKTask t)
                 jkw_team_sync<TW>(team);
             };
             // phase 3: gout += gx * gy * gz over the roots of g-set g (register tile of this lane)
-            auto contract = [&](double (&gout)[NC][NFS], const int g) {
+            auto contract = [&](double (&gout)[NC][NFS], const int g, const int bb) {
                 const double *gk = gsets + g * GSET + 2 * NROOTS;
+                // BL: bb is a compile-time constant after unrolling; else the lane's own b
+                const int gbx = (eax + (BL ? cart_x(LQ, bb) : ebx0)) * SUBP;
+                const int gby = (eay + (BL ? cart_y(LQ, bb) : eby0)) * SUBP + GSIZEP;
+                const int gbz = (eaz + (BL ? cart_z(LQ, bb) : ebz0)) * SUBP + 2 * GSIZEP;
                 const double cdx = rsgeom[0], cdy = rsgeom[1], cdz = rsgeom[2];
                 if (lane_on) {
                     if (NCS == 1) {
@@ -605,12 +614,15 @@ rys_jk_warp_kernel(JKTask t)
             auto red_a = [&](double v) {          // sum over a (lane stride NFQ*NCS), result in the a == 0 lane
 #pragma unroll
                 for (int off = 1; off < C::NFP; off <<= 1) {
-                    const double tv = __shfl_down_sync(0xffffffffu, v, off * NFQ * NCS);
+                    const double tv = __shfl_down_sync(0xffffffffu, v, off * (BL ? 1 : NFQ) * NCS);
                     if (a + off < C::NFP) v += tv;
                 }
                 return v;
             };
-            auto digest = [&](double (&gout)[NC][NFS], const int j) {
+            // digestion of the (a, bb) tile of quartet slot j.  accp / accs collect K_pr / K_ps of
+            // row a over the b loop (BL) and are flushed when `last`.
+            auto digest = [&](double (&gout)[NC][NFS], const int j, const int bb,
+                              double (&accp)[NDM][NC], double (&accs)[NDM][NFS], const bool last) {
                 const bool on = lane_on && j < nb;
                 int p0 = 0, q0 = 0;
                 if (on) {
@@ -619,13 +631,13 @@ rys_jk_warp_kernel(JKTask t)
                     q0 = pi[1];
                 }
                 const size_t prow = (size_t)(p0 + a) * nao;
-                const size_t qrow = (size_t)(q0 + b) * nao;
+                const size_t qrow = (size_t)(q0 + bb) * nao;
 #pragma unroll
                 for (int idm = 0; idm < NDM; ++idm) {
                     const double *dm = t.dm + idm * nao2;
                     if (do_j && on) {
                         double *vj = t.vj + idm * nao2;
-                        double dpq = __ldg(dm + prow + q0 + b);
+                        double dpq = __ldg(dm + prow + q0 + bb);
                         double s = 0.;
 #pragma unroll
                         for (int n = 0; n < NC; ++n) {
@@ -637,15 +649,15 @@ rys_jk_warp_kernel(JKTask t)
                                 }
                             }
                         }
-                        JK_ATOMIC_ADD(vj + prow + q0 + b, s);
+                        JK_ATOMIC_ADD(vj + prow + q0 + bb, s);
                     }
                     if (do_k) {
                         double *vk = t.vk + idm * nao2;
-                        double kpr[NC], kqr[NC], kps[NFS], kqs[NFS];
+                        double kqr[NC], kqs[NFS];
 #pragma unroll
-                        for (int n = 0; n < NC; ++n) kpr[n] = kqr[n] = 0.;
+                        for (int n = 0; n < NC; ++n) kqr[n] = 0.;
 #pragma unroll
-                        for (int d = 0; d < NFS; ++d) kps[d] = kqs[d] = 0.;
+                        for (int d = 0; d < NFS; ++d) kqs[d] = 0.;
                         if (on) {
                             double dqs[NFS], dps[NFS];
                             ld_row<NFS>(dqs, dm + qrow + s0, vec_s);
@@ -668,43 +680,46 @@ rys_jk_warp_kernel(JKTask t)
 #pragma unroll
                                     for (int d = 0; d < NFS; ++d) {
                                         const double gv = gout[n][d];
-                                        kpr[n] += gv * dqs[d];
+                                        accp[idm][n] += gv * dqs[d];
                                         kqr[n] += gv * dps[d];
-                                        kps[d] += gv * dqr[n];
+                                        accs[idm][d] += gv * dqr[n];
                                         kqs[d] += gv * dpr[n];
                                     }
                                 }
                             }
                         }
-                        bool lead_p = true, lead_q = true;      // does this lane issue the p-row / q-row atomics
-                        if (SHFL_RED) {
-                            if (NFQ > 1) {
+                        // K_q* rows: sum over a across lanes, one atomic from the a == 0 lane
+                        bool lead_q = true;
+                        if (SHFL_RED && C::NFP > 1) {
 #pragma unroll
-                                for (int n = 0; n < NC; ++n) kpr[n] = red_b(kpr[n]);
+                            for (int n = 0; n < NC; ++n) kqr[n] = red_a(kqr[n]);
 #pragma unroll
-                                for (int d = 0; d < NFS; ++d) kps[d] = red_b(kps[d]);
+                            for (int d = 0; d < NFS; ++d) kqs[d] = red_a(kqs[d]);
+                            lead_q = a == 0;
+                        }
+                        if (on && lead_q) {
+#pragma unroll
+                            for (int n = 0; n < NC; ++n)
+                                if (c0 + n < NFR) JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr[n]);
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
+                        }
+                        // K_p* rows: complete after the b loop (BL) or after the shuffle over b
+                        if (last) {
+                            bool lead_p = true;
+                            if (!BL && SHFL_RED && NFQ > 1) {
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) accp[idm][n] = red_b(accp[idm][n]);
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) accs[idm][d] = red_b(accs[idm][d]);
                                 lead_p = b == 0;
                             }
-                            if (C::NFP > 1) {
+                            if (on && lead_p) {
 #pragma unroll
-                                for (int n = 0; n < NC; ++n) kqr[n] = red_a(kqr[n]);
+                                for (int n = 0; n < NC; ++n)
+                                    if (c0 + n < NFR) JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, accp[idm][n]);
 #pragma unroll
-                                for (int d = 0; d < NFS; ++d) kqs[d] = red_a(kqs[d]);
-                                lead_q = a == 0;
-                            }
-                        }
-                        if (on) {
-#pragma unroll
-                            for (int n = 0; n < NC; ++n) {
-                                if (c0 + n < NFR) {
-                                    if (lead_p) JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, kpr[n]);
-                                    if (lead_q) JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr[n]);
-                                }
-                            }
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) {
-                                if (lead_p) JK_ATOMIC_ADD(vk + prow + s0 + d, kps[d]);
-                                if (lead_q) JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
+                                for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + prow + s0 + d, accs[idm][d]);
                             }
                         }
                     }
@@ -715,26 +730,46 @@ rys_jk_warp_kernel(JKTask t)
                 // K different quartets per lane slot, one primitive quartet each
                 build_gsets(0);
                 for (int k = 0; k < K; ++k) {
-                    double gout[NC][NFS];
+                    double accp[NDM][NC], accs[NDM][NFS];
 #pragma unroll
-                    for (int n = 0; n < NC; ++n)
+                    for (int idm = 0; idm < NDM; ++idm) {
 #pragma unroll
-                        for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
-                    contract(gout, k * NSW + s4);
-                    digest(gout, k * NSW + s4);
+                        for (int n = 0; n < NC; ++n) accp[idm][n] = 0.;
+#pragma unroll
+                        for (int d = 0; d < NFS; ++d) accs[idm][d] = 0.;
+                    }
+#pragma unroll
+                    for (int bi = 0; bi < NBL; ++bi) {
+                        const int bb = BL ? bi : b;
+                        double gout[NC][NFS];
+#pragma unroll
+                        for (int n = 0; n < NC; ++n)
+#pragma unroll
+                            for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
+                        contract(gout, k * NSW + s4, bb);
+                        digest(gout, k * NSW + s4, bb, accp, accs, bi == NBL - 1);
+                    }
                 }
             } else {
-                // contracted class: K primitive quartets of the same quartet per pass
+                // contracted class (BL == 0 only): K primitive quartets of the same quartet per pass
                 double gout[NC][NFS];
+                double accp[NDM][NC], accs[NDM][NFS];
+#pragma unroll
+                for (int idm = 0; idm < NDM; ++idm) {
+#pragma unroll
+                    for (int n = 0; n < NC; ++n) accp[idm][n] = 0.;
+#pragma unroll
+                    for (int d = 0; d < NFS; ++d) accs[idm][d] = 0.;
+                }
 #pragma unroll
                 for (int n = 0; n < NC; ++n)
 #pragma unroll
                     for (int d = 0; d < NFS; ++d) gout[n][d] = 0.;
                 for (int pass = 0; pass < npass; ++pass) {
                     build_gsets(pass);
-                    for (int k = 0; k < K; ++k) contract(gout, k * NSW + s4);
+                    for (int k = 0; k < K; ++k) contract(gout, k * NSW + s4, b);
                 }
-                digest(gout, s4);
+                digest(gout, s4, b, accp, accs, true);
             }
 
             // ---------------- keep the unprocessed remainder of the queue ----------------

@@ -57,7 +57,11 @@ CHOOSER = os.environ.get('B200_CHOOSER', 'cost')
 REG_DOUBLES = int(os.environ.get('B200_REG_DOUBLES', '180'))
 
 
-def warp_cfg_cost(y, x, ndm):
+BL_ENABLE = os.environ.get('B200_BL', '1') == '1'
+BL_GAIN = float(os.environ.get('B200_BL_GAIN', '0.85'))   # use the b-loop variant when its modelled cost is below this fraction
+
+
+def warp_cfg_cost(y, x, ndm, bl=False):
     """Instruction-count model: estimated warp instructions per quartet for lanes =
     Y pair, register tile = X pair (split NCS ways); returns (-cost, ncs) so that
     larger is better, like warp_cfg."""
@@ -75,19 +79,21 @@ def warp_cfg_cost(y, x, ndm):
         if -(-nfr // nc) != ncs:
             continue
         tile = nc * nfs
-        g = nfpq * ncs
+        g = (nf(lp) if bl else nfpq) * ncs
         if g > 256:
             break
         tw = -(-g // 32)
         nsw = 32 // g if tw == 1 else 1
         seg = lrs + 1 if ncs == 1 else sub
-        regs = tile * (1 + ndm) + (3 * sub + 3 * seg if ncs == 1 else 3 * (ls + 1))
+        regs = tile * (1 + ndm) + (3 * sub + 3 * seg if ncs == 1 else 3 * (ls + 1)) + (bl and (nc + nfs) * ndm)
         if regs > REG_DOUBLES:
             continue
         ld = 3 * ((seg + 1) // 2) if ncs == 1 else 3 * (ls + 1) * nc
         hrr = 3 * sum(lrs - d for d in range(ls)) if ncs == 1 else 0
         dig = 6 * tile * ndm + 3 * (2 * nc + 2 * nfs + 1) * ndm
         w = nroots * (ld + hrr + 2 * tile) + dig + 20
+        if bl:
+            w *= nf(lq)          # the lane loops over the nf_q components itself
         k = max(1, min(4, (32 * tw) // (nsw * 3 * nroots)))
         nab2 = (lp + 1) * (lq + 1)
         p2 = 60 + 3 * (lpq + 1) * (lrs + 1) + nab2 * ((seg + 1) // 2 + 2)
@@ -159,9 +165,24 @@ def main(dst):
                         continue
                     wc = warp_cfg((lp, lq), (lr, ls), ndm) if WARP_KERNEL else None
                     if wc is not None and (CHOOSER == 'cost' or wc[0] >= 0.3):
-                        f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
-                                '{ return jk_launch_warp<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
-                                % (name, lp, lq, lr, ls, wc[1], ndm))
+                        # uncontracted launches may use the b-loop variant (a lane owns a p
+                        # component and loops over the q components): fewer lanes per quartet
+                        bl = None
+                        if BL_ENABLE and CHOOSER == 'cost' and lq > 0:
+                            bl = warp_cfg_cost((lp, lq), (lr, ls), ndm, bl=True)
+                            # measured on Taxol: pays off for unsplit register tiles only
+                            if bl is not None and (-bl[0] > BL_GAIN * -wc[0] or bl[1] != 1):
+                                bl = None
+                        if bl is not None:
+                            f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
+                                    '{\n    if (t->nprim_p * t->nprim_q * t->nprim_r * t->nprim_s == 1)\n'
+                                    '        return jk_launch_warp<%d, %d, %d, %d, %d, %d, 1>(t, nsm, smem_max, s);\n'
+                                    '    return jk_launch_warp<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s);\n}\n'
+                                    % (name, lp, lq, lr, ls, bl[1], ndm, lp, lq, lr, ls, wc[1], ndm))
+                        else:
+                            f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
+                                    '{ return jk_launch_warp<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
+                                    % (name, lp, lq, lr, ls, wc[1], ndm))
                         decls.append((lp, lq, lr, ls, ndm, name))
                         continue
                     f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
