@@ -1,5 +1,6 @@
 // C-ABI of libgvhf_rys_b200.so (declared in include/gvhf_rys_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "rt.h"
 #include "jk_launch.cuh"
@@ -50,7 +51,13 @@ int RYS_b200_init(void)
     int dev = rt_device();
     if (dev < 0 || dev >= MAX_DEVICES) return 1;
     if (g_cheb[dev] == nullptr) {
-        g_cheb[dev] = (double *)rt_upload(RYS_CHEB_HOST, sizeof(RYS_CHEB_HOST));
+        static double *mono = nullptr;           // monomial form of the Chebyshev tables (rys_roots.cuh)
+        if (mono == nullptr) {
+            mono = (double *)malloc(sizeof(RYS_CHEB_HOST));
+            memcpy(mono, RYS_CHEB_HOST, sizeof(RYS_CHEB_HOST));
+            rys_monomial_rows(mono, RYS_CHEB_SIZE / RYS_NCHEB);
+        }
+        g_cheb[dev] = (double *)rt_upload(mono, sizeof(RYS_CHEB_HOST));
         g_large[dev] = (double *)rt_upload(RYS_LARGE_HOST, sizeof(RYS_LARGE_HOST));
         if (g_cheb[dev] == nullptr || g_large[dev] == nullptr) {
             fprintf(stderr, "RYS_b200_init: table upload failed\n");
