@@ -18,7 +18,7 @@ static inline int jk_set_chunks(JKTask *t, int workers)
     int ch = 1024;
     static const char *force = getenv("B200_YCHUNK");     // tests: exercise the chunk logic on tiny inputs
     if (force != nullptr && atoi(force) > 0) ch = atoi(force);
-    else while (ch > 128 && (long long)t->npair_x * ((t->npair_y + ch - 1) / ch) < 8LL * workers * t->world) ch >>= 1;
+    else while (ch > 32 && (long long)t->npair_x * ((t->npair_y + ch - 1) / ch) < 8LL * workers * t->world) ch >>= 1;
     t->ychunk = ch;
     t->nychunk = (t->npair_y + ch - 1) / ch;
     long long items = (long long)t->npair_x * t->nychunk;
