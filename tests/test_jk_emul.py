@@ -43,7 +43,7 @@ print('OK')
 ''' % ROOT
 
 
-@pytest.mark.parametrize('case,hermi,ychunk', [('sto', 1, 0), ('sto', 0, 3), ('sto', 2, 0), ('2', 1, 7), ('3', 0, 0), ('tz', 1, 5), ('rs', 1, 0)])
+@pytest.mark.parametrize('case,hermi,ychunk', [('sto', 1, 0), ('sto', 0, 3), ('sto', 2, 0), ('2', 1, 7), ('3', 1, 0), ('tz', 1, 5), ('rs', 1, 0)])
 def test_emulated_kernels_match_oracle(case, hermi, ychunk):
     env = dict(os.environ)
     if case == 'rs':
