@@ -19,7 +19,8 @@ __host__ __device__ constexpr int jkt_minblocks(int nf_total)
 #ifdef JKT_MINBLOCKS_FIXED
     return JKT_MINBLOCKS_FIXED;
 #endif
-    return nf_total <= 12 ? 5 : (nf_total <= 40 ? 4 : (nf_total <= 70 ? 3 : 2));
+    // measured on Taxol (profiles/): 170 registers (3 blocks) beat 96/128 for everything but the (ss|..) classes
+    return nf_total <= 6 ? 5 : (nf_total <= 70 ? 3 : 2);
 }
 
 // block-wide sum of per-thread values through shuffles + one smem stage
