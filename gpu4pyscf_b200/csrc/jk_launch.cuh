@@ -104,7 +104,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         fprintf(stderr, "rys_jk: more than %d primitive pairs per shell pair\n", JK_MAXPP);
         return 1;
     }
-    int nteams = jkw_block_threads(C::TEAM) / C::TEAM;
+    int nteams = jkw_block_threads(C::TEAM, C::TILE * (1 + NDM)) / C::TEAM;
     const int nprimq = npq * nrs;
     if (BL && nprimq != 1) {
         fprintf(stderr, "rys_jk_warp: the b-loop variant only handles uncontracted launches\n");

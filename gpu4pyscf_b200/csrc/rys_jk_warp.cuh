@@ -108,19 +108,21 @@ __device__ __forceinline__ void jkw_st_seg(double *p, const double (&src)[N])
 #define JKW_MAXTHREADS 256
 #endif
 // resident blocks per SM asked from the register allocator, by register-tile size
-__host__ __device__ constexpr int jkw_block_threads(int team)
+// Block size and resident blocks by the size d of the per-lane register tile (doubles that
+// stay live across a work item: gout + J_rs accumulators).  Measured on Taxol (profiles/):
+//   d <= 24      : 256 threads, 3 blocks (85 registers, 24 warps)
+//   24 < d <= 44 : 128 threads, 3 blocks (170 registers, 12 warps) -- X = (d,p) tiles
+//   d > 44       : 256 threads, 1 block  (255 registers, 8 warps)
+__host__ __device__ constexpr int jkw_max_threads(int d) { return (d > 24 && d <= 44) ? 128 : JKW_MAXTHREADS; }
+__host__ __device__ constexpr int jkw_block_threads(int team, int d)
 {
-    return team > JKW_MAXTHREADS ? team : (JKW_MAXTHREADS / team) * team;
+    return team > jkw_max_threads(d) ? team : (jkw_max_threads(d) / team) * team;
 }
-#ifndef JKW_MID_WARPS
-#define JKW_MID_WARPS 16     // resident warps per SM asked for mid-size register tiles (16 -> 128 registers)
-#endif
 __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int team)
 {
-    // doubles that stay live across the whole work item: gout + J_rs accumulators
     int d = tile * (1 + ndm);
-    int threads = jkw_block_threads(team);
-    int warps = d <= 24 ? 24 : (d <= 44 ? JKW_MID_WARPS : 8);      // 85 / 128 / 255 registers
+    int threads = jkw_block_threads(team, d);
+    int warps = d <= 24 ? 24 : (d <= 44 ? 12 : 8);
     (void)sub;
     int nb = warps * 32 / threads;
     return nb < 1 ? 1 : nb;
@@ -128,7 +130,8 @@ __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int 
 
 template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0>
 __global__ void
-__launch_bounds__(jkw_block_threads(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM),
+__launch_bounds__(jkw_block_threads(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM,
+                                    JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE * (1 + NDM)),
                   jkw_minblocks(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE, NDM,
                                 NCS == 1 ? JKWCfg<LP, LQ, LR, LS, NCS, BL>::SUBSIZE : LS + 1,
                                 JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM))
