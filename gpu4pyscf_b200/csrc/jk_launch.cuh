@@ -112,7 +112,10 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     }
     // g-sets per lane slot: fill (not overfill) the team in the recurrence phase,
     // whose work items are (g-set, root, axis)
-    int K = C::TEAM / (C::NSW * 3 * C::NROOTS);
+#ifndef JKW_K_BIAS
+#define JKW_K_BIAS 0
+#endif
+    int K = C::TEAM / (C::NSW * 3 * C::NROOTS) + JKW_K_BIAS;
     if (K > 4) K = 4;
     if (K < 1) K = 1;
     if (nprimq > 1 && K > nprimq) K = nprimq;
