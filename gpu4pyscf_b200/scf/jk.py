@@ -119,7 +119,7 @@ class _VHFOpt:
         # set to a dict to collect per-class kernel times (ms), like the
         # reference's _TimingCollector (jk.py:1170-1188); costs a sync per class
         self.class_timing = None
-        self.n_streams = 4
+        self.n_streams = int(os.environ.get('B200_STREAMS', '4'))
         # width (log units) of the q bins of the pair lists; 0 = exactly q-sorted lists
         self.q_bin = float(os.environ.get('B200_Q_BIN', '0.5'))
         self._streams = None
@@ -206,6 +206,17 @@ class _VHFOpt:
                     tasks.append((kb, ka, 0))      # (Y, X)
                 else:
                     tasks.append((ka, kb, 0))
+        # optional longest-processing-time order; measured slower than the natural group order on
+        # Taxol (6.77 s vs 6.63 s), so it is off by default
+        if os.environ.get('B200_SORT_TASKS', '0') == '1':
+            from . import flops
+
+            def cost(task):
+                ky, kx, _ = task
+                lprim = tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 0]) + \
+                    tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 1])
+                return len(self.bas_pair_cache[ky][0]) * len(self.bas_pair_cache[kx][0]) * flops.f_quartet(lprim)
+            tasks.sort(key=cost, reverse=True)
         self._tasks = tasks
         return tasks
 
