@@ -217,6 +217,11 @@ class _VHFOpt:
                     tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 1])
                 return len(self.bas_pair_cache[ky][0]) * len(self.bas_pair_cache[kx][0]) * flops.f_quartet(lprim)
             tasks.sort(key=cost, reverse=True)
+        mode = os.environ.get('B200_SORT_TASKS', '0')
+        if mode == '2':
+            tasks.reverse()
+        elif mode == '3':       # launches of the same kernel instantiation next to each other
+            tasks.sort(key=lambda tk: ls(tk[0]) + ls(tk[1]))
         self._tasks = tasks
         return tasks
 
