@@ -1,27 +1,33 @@
 // Warp-team variant of the direct-SCF J/K class kernel (sm_100a, FP64).
 //
 // Same arithmetic and output conventions as rys_jk_kernel (rys_jk_kernel.cuh),
-// different execution model: the unit of work is a TEAM of TW warps that owns
-// one X = (r,s) shell pair at a time, screens its own stream of Y = (p,q) pairs
-// (ballot compaction into a private queue) and evaluates NSW quartets at once
-// (TW == 1: lanes = NSW x nf_p*nf_q*NCS; TW > 1: one quartet over TW warps).
-// Teams never synchronise with each other -- the only barriers are __syncwarp
-// (TW == 1) or a named barrier over the team's warps -- so the long dependent
-// chains of the root and recurrence phases of one team overlap the FMA-dense
-// contraction/digestion phases of the other teams resident on the SM.
+// different execution model: the unit of work is a TEAM of TW warps that takes
+// (X = (r,s) shell pair, chunk of the q-ordered Y = (p,q) list) work items from a
+// device counter, screens its chunk itself (ballot compaction into a private
+// queue) and evaluates NSW quartets at once (TW == 1: lanes = NSW x G, with
+// G = nf_p*nf_q*NCS lanes per quartet, or nf_p*NCS in the b-loop variant;
+// TW > 1: one quartet over TW warps).  Teams never synchronise with each other --
+// the only barriers are __syncwarp (TW == 1) or a named barrier over the team's
+// warps -- so the dependent chains of the root and recurrence phases of one team
+// overlap the FMA-dense contraction/digestion phases of the other resident teams.
 //
 // Per pass a team holds NSW*K "g-sets" (roots, weights, 2D integrals of one
 // primitive quartet) in shared memory:
-//   uncontracted class (1 primitive quartet): K different quartets per lane slot
-//   contracted class: K primitive quartets of the same quartet
-// so that the root / VRR+TRR / HRR phases run on NSW*K*{2,3}*NROOTS lanes
-// instead of {2,3}*NROOTS.  The Rys tables of this NROOTS live in shared memory
-// (rys_roots.cuh).
+//   uncontracted launch (1 primitive quartet): K different quartets per lane slot
+//   contracted launch: K primitive quartets of the same quartet
+// and runs
+//   phase 1  one root or weight per lane (Rys series from the shared-memory tables)
+//   phase 2  one (g-set, root, axis) per lane: VRR + TRR + bra HRR in registers,
+//            result to shared memory in 16-byte segments
+//   phase 3  per lane: ket HRR in registers, gout += gx*gy*gz on its register tile
+//   phase 4  J/K digestion (K rows shuffle-reduced over the lanes of a quartet,
+//            then FP64 atomics; J_rs accumulated in registers over the work item)
 //
-// Replaces (with rys_jk_kernel for the largest classes) the reference's
-// rys_jk_kernel / rys_k_kernel / unrolled kernels
-// (gpu4pyscf/lib/gvhf-rys/rys_contract_jk.cu:33-333, unrolled_rys_jk.cu) and
-// its task generator _fill_vjk_tasks (create_tasks.cu:113-180).
+// Replaces (with rys_jk_thread_kernel for the light classes and rys_jk_kernel for
+// classes needing more than 256 lanes) the reference's rys_jk_kernel /
+// rys_k_kernel / unrolled kernels (gpu4pyscf/lib/gvhf-rys/rys_contract_jk.cu:33-333,
+// unrolled_rys_jk.cu) and its task generator _fill_vjk_tasks
+// (create_tasks.cu:113-180).
 #pragma once
 #include "common.cuh"
 #include "rys_roots.cuh"
