@@ -96,13 +96,15 @@ int B200_has_class(int lp, int lq, int lr, int ls)
     return jk_find_launcher(lp, lq, lr, ls, 1) != nullptr;
 }
 
-int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
+}   // extern "C"
+
+static int build_class_impl(double *vj, double *vk, const double *dm, int n_dm, int nao,
                         const RysIntEnvVars *envs, const int *lprim,
                         const uint32_t *pair_x, const float *q_x, int npair_x,
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
-                        double omega)
+                        double omega, double scale)
 {
     if (npair_x <= 0 || npair_y <= 0) return 0;
     if (RYS_b200_init()) return 1;
@@ -134,6 +136,7 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
         return 1;
     }
     t.omega = omega;
+    t.scale = scale;
     t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
     t.rank = rank;
     t.world = world < 1 ? 1 : world;
@@ -170,14 +173,27 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
     return 0;
 }
 
-int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
-                 RysIntEnvVars *envs, int *shls_slice, int shm_size,
-                 int npairs_ij, int npairs_kl,
-                 uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
-                 float *q_cond_ij, float *q_cond_kl,
-                 float *s_cond_ij, float *s_cond_kl,
-                 float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
-                 uint32_t *pool, int *bas, double *env)
+extern "C" {
+
+int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
+                        const RysIntEnvVars *envs, const int *lprim,
+                        const uint32_t *pair_x, const float *q_x, int npair_x,
+                        const uint32_t *pair_y, const float *q_y, int npair_y,
+                        const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
+                        int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
+                        double omega)
+{
+    return build_class_impl(vj, vk, dm, n_dm, nao, envs, lprim, pair_x, q_x, npair_x, pair_y, q_y, npair_y,
+                            dm_cond, cutoff, dm_penalty, q_margin, dedupe, rank, world, head, stream, rec_y,
+                            omega, 1.);
+}
+
+// One group quadruple with the reference's (ij|kl) argument order; scale multiplies the integrals.
+static int build_group(double *vj, double *vk, double *dm, int n_dm, int nao, RysIntEnvVars *envs,
+                       int *shls_slice, int npairs_ij, int npairs_kl,
+                       uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping, float *q_cond_ij, float *q_cond_kl,
+                       float *dm_cond, float cutoff, float dm_penalty, uint32_t *pool, int *bas,
+                       double omega, double scale)
 {
     int ish0 = shls_slice[0], jsh0 = shls_slice[2], ksh0 = shls_slice[4], lsh0 = shls_slice[6];
     int li = bas[ish0 * BAS_SLOTS + ANG_OF], lj = bas[jsh0 * BAS_SLOTS + ANG_OF];
@@ -191,20 +207,62 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
     cudaMemsetAsync(head, 0, sizeof(int), 0);
 #endif
     // orientation: whichever of (ij|kl) / (kl|ij) is instantiated (B200_has_class)
-    bool kl_is_x = B200_has_class(li, lj, lk, ll);
-    if (kl_is_x) {
+    if (B200_has_class(li, lj, lk, ll)) {
         int lprim[8] = {li, lj, lk, ll, ni, nj, nk, nl};
-        return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
-                                   pair_kl_mapping, q_cond_kl, npairs_kl,
-                                   pair_ij_mapping, q_cond_ij, npairs_ij,
-                                   dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr, nullptr, env[8]);
-    } else {
-        int lprim[8] = {lk, ll, li, lj, nk, nl, ni, nj};
-        return B200_build_jk_class(vj, vk, dm, n_dm, nao, envs, lprim,
-                                   pair_ij_mapping, q_cond_ij, npairs_ij,
-                                   pair_kl_mapping, q_cond_kl, npairs_kl,
-                                   dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr, nullptr, env[8]);
+        return build_class_impl(vj, vk, dm, n_dm, nao, envs, lprim,
+                                pair_kl_mapping, q_cond_kl, npairs_kl, pair_ij_mapping, q_cond_ij, npairs_ij,
+                                dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr, nullptr, omega, scale);
     }
+    int lprim[8] = {lk, ll, li, lj, nk, nl, ni, nj};
+    return build_class_impl(vj, vk, dm, n_dm, nao, envs, lprim,
+                            pair_ij_mapping, q_cond_ij, npairs_ij, pair_kl_mapping, q_cond_kl, npairs_kl,
+                            dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr, nullptr, omega, scale);
+}
+
+int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
+                 RysIntEnvVars *envs, int *shls_slice, int shm_size,
+                 int npairs_ij, int npairs_kl,
+                 uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
+                 float *q_cond_ij, float *q_cond_kl,
+                 float *s_cond_ij, float *s_cond_kl,
+                 float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
+                 uint32_t *pool, int *bas, double *env)
+{
+    (void)shm_size; (void)s_cond_ij; (void)s_cond_kl; (void)diffuse_exps;
+    return build_group(vj, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
+                       pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
+                       dm_cond, cutoff, dm_penalty, pool, bas, env[8], 1.);
+}
+
+// K only, with range separation: lr_factor * K[erf(|omega| r)/r] + sr_factor * K[erfc(|omega| r)/r]
+// = sr_factor * K[1/r] + (lr_factor - sr_factor) * K[erf(|omega| r)/r]; omega == 0: plain K.
+int RYS_build_k(double *vk, double *dm, int n_dm, int nao, double omega, double lr_factor, double sr_factor,
+                RysIntEnvVars *envs, int *shls_slice, int shm_size, int npairs_ij, int npairs_kl,
+                uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
+                float *q_cond_ij, float *q_cond_kl, float *s_cond_ij, float *s_cond_kl,
+                float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
+                uint32_t *pool, int *bas)
+{
+    (void)shm_size; (void)s_cond_ij; (void)s_cond_kl; (void)diffuse_exps;
+    double c_full = 1., c_lr = 0.;
+    if (omega != 0.) {
+        c_full = sr_factor;
+        c_lr = lr_factor - sr_factor;
+    }
+    const double w = omega < 0. ? -omega : omega;
+    if (c_full != 0.) {
+        int err = build_group(nullptr, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
+                              pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
+                              dm_cond, cutoff, dm_penalty, pool, bas, 0., c_full);
+        if (err) return err;
+    }
+    if (c_lr != 0.) {
+        int err = build_group(nullptr, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
+                              pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
+                              dm_cond, cutoff, dm_penalty, pool, bas, w, c_lr);
+        if (err) return err;
+    }
+    return 0;
 }
 
 int B200_qcond(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,

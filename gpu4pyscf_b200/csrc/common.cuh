@@ -68,6 +68,7 @@ struct JKTask {
     unsigned long long *counter;  // optional: number of quartets evaluated (measurement)
     int nq;                 // quartet slots per block
     int slot_doubles;       // shared-memory doubles per slot
+    double scale;           // factor applied to every integral (lr/sr mixing of RYS_build_k); 1 by default
     double omega;           // 0: 1/r; > 0: long-range erf(omega r)/r (reference: rys_roots_rs, rys_roots.cu:91-119)
     const double *rec_y;    // optional per-pair records of the Y list (pair_record_kernel), or null
     int rec_stride;         // doubles per record

@@ -285,7 +285,7 @@ rys_jk_kernel(JKTask t)
                     if (tg == 0) {
                         sl[SLOT_AB + 0] = dx; sl[SLOT_AB + 1] = dy; sl[SLOT_AB + 2] = dz;
                         sl[SLOT_A + 0] = Rp[0]; sl[SLOT_A + 1] = Rp[1]; sl[SLOT_A + 2] = Rp[2];
-                        double fac = PI_FAC;
+                        double fac = PI_FAC * t.scale;
                         if (psh == qsh) fac *= .5;
                         if (rsh == ssh) fac *= .5;
                         if (pair_pq == pair_rs) fac *= .5;

@@ -190,7 +190,7 @@ rys_jk_thread_kernel(JKTask t)
                 // caller provides one, else from bas/env (reference-signature entry)
                 const double *rec = t.rec_y != nullptr ? t.rec_y + (size_t)iy * t.rec_stride : nullptr;
                 int p0, q0;
-                double Ax, Ay, Az, ABx, ABy, ABz, fac = PI_FAC, rr2 = 0.;
+                double Ax, Ay, Az, ABx, ABy, ABz, fac = PI_FAC * t.scale, rr2 = 0.;
                 const double *ep = nullptr, *eq = nullptr, *cp = nullptr, *cq = nullptr;
                 if (rec != nullptr) {
                     const double2 h0 = *(const double2 *)(rec + 0);

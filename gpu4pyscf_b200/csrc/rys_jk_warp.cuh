@@ -362,7 +362,7 @@ rys_jk_warp_kernel(JKTask t)
                     if (ip == 0) {
                         sl[0] = rec[0]; sl[1] = rec[1]; sl[2] = rec[2];
                         sl[3] = rec[3]; sl[4] = rec[4]; sl[5] = rec[5];
-                        double fac = PI_FAC * rec[7];
+                        double fac = PI_FAC * t.scale * rec[7];
                         if (rsh == ssh) fac *= .5;
                         if (t.dedupe == 1 && iy == ix) fac *= .5;
                         sl[6] = active ? fac : 0.;
@@ -394,7 +394,7 @@ rys_jk_warp_kernel(JKTask t)
                 if (ip == 0) {
                     sl[0] = dx; sl[1] = dy; sl[2] = dz;
                     sl[3] = Rp[0]; sl[4] = Rp[1]; sl[5] = Rp[2];
-                    double fac = PI_FAC;
+                    double fac = PI_FAC * t.scale;
                     if (psh == qsh) fac *= .5;
                     if (rsh == ssh) fac *= .5;
                     if (pair_pq == pair_rs) fac *= .5;

@@ -61,6 +61,10 @@ def load_library(name='libgvhf_rys_b200'):
         vp, vp, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp, vp]
     lib.B200_has_class.restype = c_int
     lib.B200_has_class.argtypes = [c_int, c_int, c_int, c_int]
+    lib.RYS_build_k.restype = c_int
+    lib.RYS_build_k.argtypes = [
+        vp, vp, c_int, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp, c_int, c_int, c_int,
+        vp, vp, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp]
     lib.B200_qcond.restype = c_int
     lib.B200_qcond.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
     lib.B200_set_counter.restype = c_int

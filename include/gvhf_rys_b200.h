@@ -64,6 +64,20 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
                  float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
                  uint32_t *pool, int *bas, double *env);
 
+/* Reference signature: RYS_build_k, lib/gvhf-rys/rys_contract_k.cu:605-709, called from
+ * gpu4pyscf/scf/jk.py:845-877.  K only; omega == 0: plain exchange (the factors are
+ * ignored); omega != 0: lr_factor * K[erf(|omega| r)/r] + sr_factor * K[erfc(|omega| r)/r],
+ * evaluated as sr_factor * K[1/r] + (lr_factor - sr_factor) * K[erf] (one or two launches).
+ * Same group / pair-list / de-duplication semantics as RYS_build_jk; s_cond_*,
+ * diffuse_exps and shm_size are accepted and ignored (the full-range q_cond is a valid
+ * Schwarz bound for the attenuated operators). */
+int RYS_build_k(double *vk, double *dm, int n_dm, int nao, double omega, double lr_factor, double sr_factor,
+                RysIntEnvVars *envs, int *shls_slice, int shm_size, int npairs_ij, int npairs_kl,
+                uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
+                float *q_cond_ij, float *q_cond_kl, float *s_cond_ij, float *s_cond_kl,
+                float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
+                uint32_t *pool, int *bas);
+
 /* Native entry: one angular class (pq|rs).
  *   lprim  HOST int[8] = {lp, lq, lr, ls, nprim_p, nprim_q, nprim_r, nprim_s}
  *   X = (r,s) pair list (block-resident side, nf_r*nf_s >= nf_p*nf_q),

@@ -286,3 +286,51 @@ def test_range_separated_k_factors():
     rk = (0.65 * oracle.get_jk(mol, dm, hermi=1, omega=0.4)[1]
           + 0.2 * oracle.get_jk(mol, dm, hermi=1, omega=-0.4)[1])
     assert abs(vk.cpu().numpy() - rk).max() < 1e-10 * max(1., abs(rk).max())
+
+
+def test_rys_build_k_reference_signature():
+    """RYS_build_k with the reference's argument list (jk.py:845-877): K only, range
+    separation through (omega, lr_factor, sr_factor), per-group launch loop."""
+    import ctypes
+    import math
+    from gpu4pyscf_b200.scf import jk
+    from gpu4pyscf_b200.lib import loader
+    lib = loader.load_library()
+    mol = molecules.water('def2-tzvp')
+    np.random.seed(8)
+    nao = mol.nao
+    dm = np.random.rand(nao, nao)
+    dm = dm + dm.T
+    opt = jk._VHFOpt(mol).build()
+    smol = opt.sorted_mol
+    dms = opt.apply_coeff_C_mat_CT(torch.as_tensor(dm, device=opt.device)[None]).contiguous()
+    nbas, naos = smol.nbas, smol.nao
+    dm_cond = torch.empty((nbas, nbas), dtype=torch.float32, device=opt.device)
+    lib.B200_condense(jk._ptr(dm_cond), jk._ptr(dms), 1, naos, jk._ptr(opt.rys_envs._keep[3]), nbas, None)
+    offs = np.append(0, np.cumsum(smol.l_ctr_counts))
+    ng = len(smol.l_ctr_counts)
+    bas_host = np.ascontiguousarray(smol._bas, dtype=np.int32)
+    cutoff = math.log(1e-13)
+    pool = torch.zeros(16, dtype=torch.int32, device=opt.device)
+    omega, lr, sr = 0.4, 0.65, 0.2
+    vk = torch.zeros_like(dms)
+    dmax = float(dm_cond.max())
+    torch.cuda.synchronize()
+    for i in range(ng):
+        for j in range(i + 1):
+            for k in range(i + 1):
+                for l in range(k + 1):
+                    pij, qij = opt.bas_pair_cache[i, j][:2]
+                    pkl, qkl = opt.bas_pair_cache[k, l][:2]
+                    shls = (ctypes.c_int * 8)(offs[i], offs[i + 1], offs[j], offs[j + 1],
+                                              offs[k], offs[k + 1], offs[l], offs[l + 1])
+                    err = lib.RYS_build_k(
+                        jk._ptr(vk), jk._ptr(dms), 1, naos, omega, lr, sr, ctypes.byref(opt.rys_envs), shls, 0,
+                        len(pij), len(pkl), jk._ptr(pij), jk._ptr(pkl), jk._ptr(qij), jk._ptr(qkl),
+                        jk._ptr(qij), jk._ptr(qkl), None, jk._ptr(dm_cond), cutoff, dmax, jk._ptr(pool),
+                        bas_host.ctypes.data_as(ctypes.c_void_p))
+                    assert err == 0
+    torch.cuda.synchronize()
+    vk = vk + vk.transpose(1, 2)
+    ref = opt.get_k(dms, 1, omega=omega, lr_factor=lr, sr_factor=sr)
+    assert abs(vk - ref).max() < 1e-10

@@ -1,0 +1,76 @@
+"""Reference-signature entry points RYS_build_jk / RYS_build_k (gpu4pyscf/scf/jk.py:564-583,
+845-877) driven exactly like the reference's per-group launch loop, through the SIMT
+emulator build of the kernels (CPU only)."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import os, sys, ctypes, math
+os.environ['GPU4PYSCF_B200_EMUL'] = '1'
+sys.path.insert(0, %r)
+import numpy as np
+import torch
+from gpu4pyscf_b200.csrc import build
+build.build(emul=True)
+from gpu4pyscf_b200.scf import jk
+from gpu4pyscf_b200.lib import loader
+from tests import molecules
+lib = loader.load_library()
+mol = molecules.water('def2-svp')
+np.random.seed(7)
+nao = mol.nao
+dm = np.random.rand(nao, nao)
+dm = dm + dm.T
+opt = jk._VHFOpt(mol).build()
+smol = opt.sorted_mol
+dms = opt.apply_coeff_C_mat_CT(torch.as_tensor(dm)[None]).contiguous()
+nbas, naos = smol.nbas, smol.nao
+dm_cond = torch.empty((nbas, nbas), dtype=torch.float32)
+lib.B200_condense(jk._ptr(dm_cond), jk._ptr(dms), 1, naos, jk._ptr(opt.rys_envs._keep[3]), nbas, None)
+offs = np.append(0, np.cumsum(smol.l_ctr_counts))
+ng = len(smol.l_ctr_counts)
+bas_host = np.ascontiguousarray(smol._bas, dtype=np.int32)
+cutoff = math.log(1e-13)
+pool = torch.zeros(16, dtype=torch.int32)
+omega, lr, sr = 0.4, 0.65, 0.2
+
+def loop(fn):
+    for i in range(ng):
+        for j in range(i + 1):
+            for k in range(i + 1):
+                for l in range(k + 1):
+                    pij, qij = opt.bas_pair_cache[i, j][:2]
+                    pkl, qkl = opt.bas_pair_cache[k, l][:2]
+                    shls = (ctypes.c_int * 8)(offs[i], offs[i + 1], offs[j], offs[j + 1],
+                                              offs[k], offs[k + 1], offs[l], offs[l + 1])
+                    assert fn(shls, pij, qij, pkl, qkl) == 0
+
+vk = torch.zeros_like(dms)
+loop(lambda shls, pij, qij, pkl, qkl: lib.RYS_build_k(
+    jk._ptr(vk), jk._ptr(dms), 1, naos, omega, lr, sr, ctypes.byref(opt.rys_envs), shls, 0,
+    len(pij), len(pkl), jk._ptr(pij), jk._ptr(pkl), jk._ptr(qij), jk._ptr(qkl), jk._ptr(qij), jk._ptr(qkl),
+    None, jk._ptr(dm_cond), cutoff, float(dm_cond.max()), jk._ptr(pool),
+    bas_host.ctypes.data_as(ctypes.c_void_p)))
+vk = vk + vk.transpose(1, 2)
+ref = opt.get_k(dms, 1, omega=omega, lr_factor=lr, sr_factor=sr)
+assert abs(vk - ref).max() < 1e-11, abs(vk - ref).max()
+
+vk0 = torch.zeros_like(dms)
+loop(lambda shls, pij, qij, pkl, qkl: lib.RYS_build_k(
+    jk._ptr(vk0), jk._ptr(dms), 1, naos, 0., 0., 0., ctypes.byref(opt.rys_envs), shls, 0,
+    len(pij), len(pkl), jk._ptr(pij), jk._ptr(pkl), jk._ptr(qij), jk._ptr(qkl), jk._ptr(qij), jk._ptr(qkl),
+    None, jk._ptr(dm_cond), cutoff, float(dm_cond.max()), jk._ptr(pool),
+    bas_host.ctypes.data_as(ctypes.c_void_p)))
+vk0 = vk0 + vk0.transpose(1, 2)
+ref0 = opt.get_k(dms, 1)
+assert abs(vk0 - ref0).max() < 1e-11, abs(vk0 - ref0).max()
+print('OK')
+''' % ROOT
+
+
+def test_rys_build_k_reference_signature():
+    r = subprocess.run([sys.executable, '-c', SCRIPT], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
