@@ -173,7 +173,110 @@ static int build_class_impl(double *vj, double *vk, const double *dm, int n_dm, 
     return 0;
 }
 
+// Row-stream launch of one angular class: Y = rows of (p,q) pairs (q streamed over lanes), X = (r,s).
+static int build_rows_impl(double *vj, double *vk, double *vkT, const double *dm, const double *dmT,
+                           int n_dm, int nao, const RysIntEnvVars *envs, const int *lprim,
+                           const uint32_t *pair_x, const float *q_x, int npair_x,
+                           const uint32_t *pair_y, const float *q_y, const double *rec_y,
+                           const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
+                           const float *dm_cond, float cutoff, float dm_penalty,
+                           int dedupe, int rank, int world, unsigned long long *head, void *stream,
+                           double omega, double scale)
+{
+    if (npair_x <= 0 || nrows <= 0) return 0;
+    if (RYS_b200_init()) return 1;
+    int dev = rt_device();
+    int lp = lprim[0], lq = lprim[1], lr = lprim[2], ls = lprim[3];
+    if (omega < 0.) {
+        fprintf(stderr, "B200_build_jk_rows: omega < 0 (short range) is composed by the caller\n");
+        return 1;
+    }
+    if (rec_y == nullptr || (vk != nullptr && (vkT == nullptr || dmT == nullptr))) {
+        fprintf(stderr, "B200_build_jk_rows: rec_y, dmT and vkT are required\n");
+        return 1;
+    }
+    JKTask t;
+    memset(&t, 0, sizeof(t));
+    t.nao = nao;
+    t.nbas = envs->nbas;
+    t.bas = envs->bas;
+    t.env = envs->env;
+    t.ao_loc = envs->ao_loc;
+    t.pair_x = pair_x; t.pair_y = pair_y;
+    t.q_x = q_x; t.q_y = q_y;
+    t.npair_x = npair_x;
+    t.npair_y = 0;
+    t.row_ptr = row_ptr; t.row_p = row_p; t.row_qmax = row_qmax; t.nrows = nrows;
+    t.dm_cond = dm_cond;
+    t.cutoff = cutoff;
+    t.dm_penalty = dm_penalty;
+    t.dedupe = dedupe;
+    t.head = (int *)head;
+    t.rec_y = rec_y;
+    t.omega = omega;
+    t.scale = scale;
+    t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
+    t.rank = rank;
+    t.world = world < 1 ? 1 : world;
+    t.nprim_p = lprim[4]; t.nprim_q = lprim[5]; t.nprim_r = lprim[6]; t.nprim_s = lprim[7];
+    t.rys_cheb = g_cheb[dev];
+    t.rys_large = g_large[dev];
+    t.counter = g_counter;
+    int nsm = rt_num_sm();
+    int smem_max = rt_smem_max();
+    size_t nao2 = (size_t)nao * nao;
+    int i0 = 0;
+    while (i0 < n_dm) {
+        int ndm = (n_dm - i0 >= 2) ? 2 : 1;
+        jk_launcher_t fn = jk_find_row_launcher(lp, lq, lr, ls, ndm);
+        if (fn == nullptr && ndm == 2) {
+            ndm = 1;
+            fn = jk_find_row_launcher(lp, lq, lr, ls, ndm);
+        }
+        if (fn == nullptr) {
+            fprintf(stderr, "B200_build_jk_rows: no row-stream kernel for class (%d%d|%d%d)\n", lp, lq, lr, ls);
+            return 1;
+        }
+        t.vj = vj ? vj + i0 * nao2 : nullptr;
+        t.vk = vk ? vk + i0 * nao2 : nullptr;
+        t.vkT = vk ? vkT + i0 * nao2 : nullptr;
+        t.dm = dm + i0 * nao2;
+        t.dmT = dmT ? dmT + i0 * nao2 : nullptr;
+        t.n_dm = ndm;
+        if (i0 > 0) {
+#ifdef CPU_EMUL
+            *head = 0;
+#else
+            cudaMemsetAsync(head, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+#endif
+        }
+        if (fn(&t, nsm, smem_max, (cudaStream_t)stream)) return 1;
+        i0 += ndm;
+    }
+    return 0;
+}
+
 extern "C" {
+
+int B200_has_row_class(int lp, int lq, int lr, int ls)
+{
+    if (lp < 0 || lq < 0 || lr < 0 || ls < 0) return 0;
+    if (lp > LMAX_B200 || lq > LMAX_B200 || lr > LMAX_B200 || ls > LMAX_B200) return 0;
+    return jk_find_row_launcher(lp, lq, lr, ls, 1) != nullptr;
+}
+
+int B200_build_jk_rows(double *vj, double *vk, double *vkT, const double *dm, const double *dmT,
+                       int n_dm, int nao, const RysIntEnvVars *envs, const int *lprim,
+                       const uint32_t *pair_x, const float *q_x, int npair_x,
+                       const uint32_t *pair_y, const float *q_y, const double *rec_y,
+                       const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
+                       const float *dm_cond, float cutoff, float dm_penalty,
+                       int dedupe, int rank, int world, unsigned long long *head, void *stream, double omega)
+{
+    return build_rows_impl(vj, vk, vkT, dm, dmT, n_dm, nao, envs, lprim, pair_x, q_x, npair_x,
+                           pair_y, q_y, rec_y, row_ptr, row_p, row_qmax, nrows,
+                           dm_cond, cutoff, dm_penalty, dedupe, rank, world, head, stream, omega, 1.);
+}
 
 int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
                         const RysIntEnvVars *envs, const int *lprim,

@@ -74,6 +74,16 @@ struct JKTask {
     int rec_stride;         // doubles per record
     int ychunk;             // work item = (X pair, chunk of `ychunk` consecutive Y candidates)
     int nychunk;            // ceil(npair_y / ychunk)
+    // ---- row-stream kernels (rys_jk_rowt.cuh, rys_jk_roww.cuh): the Y list is grouped in rows
+    // (all partners q of one shell p are consecutive, pair_y = p*nbas+q in (p,q) = kernel order)
+    const int *row_ptr;     // [nrows + 1] offsets into pair_y / q_y / rec_y
+    const int *row_p;       // [nrows] the shell p of each row
+    const float *row_qmax;  // [nrows] largest q_y of the row
+    int nrows;
+    int rows_per_item;      // work item = (X pair, block of rows_per_item consecutive rows)
+    int nrowblk;            // ceil(nrows / rows_per_item)
+    const double *dmT;      // [n_dm, nao, nao] transposed density matrices (== dm when D is symmetric)
+    double *vkT;            // [n_dm, nao, nao] receives the q-row K blocks transposed (== vk for symmetric D)
 };
 
 // Per-pair record (precomputed once per _VHFOpt.build, in pair-list order):

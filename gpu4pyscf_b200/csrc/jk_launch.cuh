@@ -6,6 +6,7 @@
 #include "rys_jk_kernel.cuh"
 #include "rys_jk_thread.cuh"
 #include "rys_jk_warp.cuh"
+#include "rys_jk_rowt.cuh"
 
 
 typedef int (*jk_launcher_t)(JKTask *t, int nsm, int smem_max, cudaStream_t stream);
@@ -147,4 +148,46 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     if (grid < 1) return 0;
     KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_warp_kernel");
+}
+
+// Work items of a row-stream launch: (X pair, block of consecutive rows).  Enough items for
+// `workers` independent warps/teams, few enough that the per-item X setup and the J_rs flush
+// stay amortised.
+static inline long long jk_set_rowblocks(JKTask *t, int workers)
+{
+    int rpi = 16;
+    static const char *force = getenv("B200_ROWS_PER_ITEM");   // tests: exercise the block logic on tiny inputs
+    if (force != nullptr && atoi(force) > 0) rpi = atoi(force);
+    else while (rpi > 1 && (long long)t->npair_x * ((t->nrows + rpi - 1) / rpi) < 16LL * workers * t->world) rpi >>= 1;
+    t->rows_per_item = rpi;
+    t->nrowblk = (t->nrows + rpi - 1) / rpi;
+    long long items = (long long)t->npair_x * t->nrowblk;
+    return (items + t->world - 1) / t->world;
+}
+
+// thread-per-quartet row-stream kernel (light classes)
+template <int LP, int LQ, int LR, int LS, int NDM>
+int jk_launch_rowt(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
+{
+    typedef JKCfg<LP, LQ, LR, LS, 1> C;
+    int npq = t->nprim_p * t->nprim_q;
+    int nrs = t->nprim_r * t->nprim_s;
+    if (npq > JK_MAXPP || nrs > JK_MAXPP) {
+        fprintf(stderr, "rys_jk: more than %d primitive pairs per shell pair\n", JK_MAXPP);
+        return 1;
+    }
+    int nt = JKT_THREADS;
+    int smem = (RysSmem<C::NROOTS>::DOUBLES
+                + (nt / 32) * jkrt_warp_doubles(nrs, NDM, C::NFRS, C::NFP, C::NFR, C::NFS)) * 8;
+    int per_sm = rt_prepare(rys_jk_rowt_kernel<LP, LQ, LR, LS, NDM>, smem, nt);
+    if (per_sm < 1) {
+        fprintf(stderr, "rys_jk_rowt: class (%d%d|%d%d) cannot be made resident\n", LP, LQ, LR, LS);
+        return 1;
+    }
+    int grid = nsm * per_sm;
+    long long nitems = jk_set_rowblocks(t, grid * (nt / 32));
+    if ((long long)grid * (nt / 32) > nitems) grid = (int)((nitems + nt / 32 - 1) / (nt / 32));
+    if (grid < 1) return 0;
+    KLAUNCH((rys_jk_rowt_kernel<LP, LQ, LR, LS, NDM>), grid, nt, smem, stream, *t);
+    return rt_last_error("rys_jk_rowt_kernel");
 }

@@ -37,6 +37,129 @@ __host__ __device__ inline int jkt_warp_doubles(int nrs, int ndm, int nfrs)
     return (2 + nrs * 5 + ndm * nfrs + 32 + 1) & ~1;
 }
 
+// One primitive quartet of (pq|rs): Rys roots and weights, VRR + TRR + both HRRs in
+// registers, gout[((a*NFQ+b)*NFR+c)*NFS+d] += gx*gy*gz.  (zeta, P) is the Gaussian
+// product of the (p,q) primitive pair with prefactor cpq, rr = {eta, Qx, Qy, Qz, coef}
+// that of the (r,s) pair; A / C are the centres of p / r, AB = A - B, CD = C - D.
+// Recurrences as in the reference (build_rys_gxyz.cuh:18-123), different data flow.
+template <int LP, int LQ, int LR, int LS>
+__device__ __forceinline__ void jkt_prim_quartet(
+    double (&gout)[ncart(LP) * ncart(LQ) * ncart(LR) * ncart(LS)],
+    const double zeta, const double Px, const double Py, const double Pz, const double cpq,
+    const double Ax, const double Ay, const double Az, const double ABx, const double ABy, const double ABz,
+    const double *rr, const double Cx, const double Cy, const double Cz,
+    const double CDx, const double CDy, const double CDz, const double omega, const double *rys_tab)
+{
+    typedef JKCfg<LP, LQ, LR, LS, 1> C;
+    constexpr int NFP = C::NFP, NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS;
+    constexpr int LPQ = C::LPQ, LRS = C::LRS, NROOTS = C::NROOTS;
+    const double eta = rr[0];
+    const double PQx = Px - rr[1], PQy = Py - rr[2], PQz = Pz - rr[3];
+    const double ze = zeta + eta;
+    const double zei = 1. / ze;
+    const double theta = zeta * eta * zei;
+    double x = theta * (PQx * PQx + PQy * PQy + PQz * PQz);
+    double pref = cpq * rr[4] / (zeta * eta * sqrt(ze));
+    double rscale = zei;
+    if (omega != 0.) {                   // long-range erf(omega r)/r: theta -> theta * lrf
+        const double lrf = omega * omega / (omega * omega + theta);
+        x *= lrf;
+        rscale *= lrf;
+        pref *= sqrt(lrf);
+    }
+    const double hz = .5 / zeta, he = .5 / eta;
+#pragma unroll
+    for (int root = 0; root < NROOTS; ++root) {
+        const double rt_aa = rys_value_s<NROOTS>(root, x, rys_tab) * rscale;
+        const double wt = rys_value_s<NROOTS>(NROOTS + root, x, rys_tab) * pref;
+        const double rt_aij = rt_aa * eta;
+        const double rt_akl = rt_aa * zeta;
+        const double b00 = .5 * rt_aa;
+        const double b10 = hz * (1. - rt_aij);
+        const double b01 = he * (1. - rt_akl);
+        double g4[3][C::GSIZE];
+#pragma unroll
+        for (int axis = 0; axis < 3; ++axis) {
+            const double PQ = axis == 0 ? PQx : (axis == 1 ? PQy : PQz);
+            const double PA = axis == 0 ? Px - Ax : (axis == 1 ? Py - Ay : Pz - Az);
+            const double QC = axis == 0 ? rr[1] - Cx : (axis == 1 ? rr[2] - Cy : rr[3] - Cz);
+            const double AB = axis == 0 ? ABx : (axis == 1 ? ABy : ABz);
+            const double CD = axis == 0 ? CDx : (axis == 1 ? CDy : CDz);
+            const double c0p = PA - rt_aij * PQ;
+            const double c0q = QC + rt_akl * PQ;
+            double g[LRS + 1][LPQ + 1];
+            g[0][0] = (axis == 2) ? wt : 1.;
+            if (LPQ > 0) {
+                g[0][1] = c0p * g[0][0];
+#pragma unroll
+                for (int e = 1; e < LPQ; ++e)
+                    g[0][e + 1] = c0p * g[0][e] + e * b10 * g[0][e - 1];
+            }
+            if (LRS > 0) {
+                g[1][0] = c0q * g[0][0];
+#pragma unroll
+                for (int e = 1; e <= LPQ; ++e)
+                    g[1][e] = c0q * g[0][e] + e * b00 * g[0][e - 1];
+#pragma unroll
+                for (int f = 1; f < LRS; ++f) {
+                    g[f + 1][0] = c0q * g[f][0] + f * b01 * g[f - 1][0];
+#pragma unroll
+                    for (int e = 1; e <= LPQ; ++e)
+                        g[f + 1][e] = c0q * g[f][e] + f * b01 * g[f - 1][e] + e * b00 * g[f][e - 1];
+                }
+            }
+            // bra HRR into u[b][a][f], then ket HRR
+            double u[LQ + 1][LP + 1][LRS + 1];
+#pragma unroll
+            for (int f = 0; f <= LRS; ++f) {
+                double w[LPQ + 1];
+#pragma unroll
+                for (int a = 0; a <= LPQ; ++a) w[a] = g[f][a];
+#pragma unroll
+                for (int b = 0; b <= LQ; ++b) {
+#pragma unroll
+                    for (int a = 0; a <= LP; ++a) u[b][a][f] = w[a];
+                    if (b < LQ) {
+#pragma unroll
+                        for (int a = 0; a < LPQ - b; ++a) w[a] = w[a + 1] + AB * w[a];
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a <= LP; ++a)
+#pragma unroll
+                for (int b = 0; b <= LQ; ++b) {
+                    double v[LRS + 1];
+#pragma unroll
+                    for (int f = 0; f <= LRS; ++f) v[f] = u[b][a][f];
+#pragma unroll
+                    for (int d = 0; d <= LS; ++d) {
+#pragma unroll
+                        for (int c = 0; c <= LR; ++c)
+                            g4[axis][((a * (LQ + 1) + b) * (LR + 1) + c) * (LS + 1) + d] = v[c];
+                        if (d < LS) {
+#pragma unroll
+                            for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                        }
+                    }
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < NFP; ++a)
+#pragma unroll
+        for (int b = 0; b < NFQ; ++b)
+#pragma unroll
+        for (int c = 0; c < NFR; ++c)
+#pragma unroll
+        for (int d = 0; d < NFS; ++d) {
+            gout[((a * NFQ + b) * NFR + c) * NFS + d] +=
+                g4[0][((cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * (LR + 1) + cart_x(LR, c)) * (LS + 1) + cart_x(LS, d)]
+              * g4[1][((cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * (LR + 1) + cart_y(LR, c)) * (LS + 1) + cart_y(LS, d)]
+              * g4[2][((cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * (LR + 1) + cart_z(LR, c)) * (LS + 1) + cart_z(LS, d)];
+        }
+    }
+}
+
 template <int LP, int LQ, int LR, int LS, int NDM>
 __global__ void
 __launch_bounds__(JKT_THREADS, jkt_minblocks(ncart(LP) * ncart(LQ) * ncart(LR) * ncart(LS) + ncart(LR) * ncart(LS) * NDM))
@@ -242,114 +365,10 @@ rys_jk_thread_kernel(JKTask t)
                         Px = Ax - fq * ABx; Py = Ay - fq * ABy; Pz = Az - fq * ABz;
                         cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
                     }
-                    for (int irs = 0; irs < nrs; ++irs) {
-                        const double *rr = rsprim + irs * 5;
-                        const double eta = rr[0];
-                        const double PQx = Px - rr[1], PQy = Py - rr[2], PQz = Pz - rr[3];
-                        const double ze = zeta + eta;
-                        const double zei = 1. / ze;
-                        const double theta = zeta * eta * zei;
-                        double x = theta * (PQx * PQx + PQy * PQy + PQz * PQz);
-                        double pref = cpq * rr[4] / (zeta * eta * sqrt(ze));
-                        double rscale = zei;
-                        if (t.omega != 0.) {                   // long-range erf(omega r)/r: theta -> theta * lrf
-                            const double lrf = t.omega * t.omega / (t.omega * t.omega + theta);
-                            x *= lrf;
-                            rscale *= lrf;
-                            pref *= sqrt(lrf);
-                        }
-                        const double hz = .5 / zeta, he = .5 / eta;
-#pragma unroll
-                        for (int root = 0; root < NROOTS; ++root) {
-                            const double rt_aa = rys_value_s<NROOTS>(root, x, rys_tab) * rscale;
-                            const double wt = rys_value_s<NROOTS>(NROOTS + root, x, rys_tab) * pref;
-                            const double rt_aij = rt_aa * eta;
-                            const double rt_akl = rt_aa * zeta;
-                            const double b00 = .5 * rt_aa;
-                            const double b10 = hz * (1. - rt_aij);
-                            const double b01 = he * (1. - rt_akl);
-                            double g4[3][C::GSIZE];
-#pragma unroll
-                            for (int axis = 0; axis < 3; ++axis) {
-                                const double PQ = axis == 0 ? PQx : (axis == 1 ? PQy : PQz);
-                                const double PA = axis == 0 ? Px - Ax : (axis == 1 ? Py - Ay : Pz - Az);
-                                const double QC = axis == 0 ? rr[1] - Cx : (axis == 1 ? rr[2] - Cy : rr[3] - Cz);
-                                const double AB = axis == 0 ? ABx : (axis == 1 ? ABy : ABz);
-                                const double CD = axis == 0 ? CDx : (axis == 1 ? CDy : CDz);
-                                const double c0p = PA - rt_aij * PQ;
-                                const double c0q = QC + rt_akl * PQ;
-                                double g[LRS + 1][LPQ + 1];
-                                g[0][0] = (axis == 2) ? wt : 1.;
-                                if (LPQ > 0) {
-                                    g[0][1] = c0p * g[0][0];
-#pragma unroll
-                                    for (int e = 1; e < LPQ; ++e)
-                                        g[0][e + 1] = c0p * g[0][e] + e * b10 * g[0][e - 1];
-                                }
-                                if (LRS > 0) {
-                                    g[1][0] = c0q * g[0][0];
-#pragma unroll
-                                    for (int e = 1; e <= LPQ; ++e)
-                                        g[1][e] = c0q * g[0][e] + e * b00 * g[0][e - 1];
-#pragma unroll
-                                    for (int f = 1; f < LRS; ++f) {
-                                        g[f + 1][0] = c0q * g[f][0] + f * b01 * g[f - 1][0];
-#pragma unroll
-                                        for (int e = 1; e <= LPQ; ++e)
-                                            g[f + 1][e] = c0q * g[f][e] + f * b01 * g[f - 1][e] + e * b00 * g[f][e - 1];
-                                    }
-                                }
-                                // bra HRR into u[b][a][f], then ket HRR
-                                double u[LQ + 1][LP + 1][LRS + 1];
-#pragma unroll
-                                for (int f = 0; f <= LRS; ++f) {
-                                    double w[LPQ + 1];
-#pragma unroll
-                                    for (int a = 0; a <= LPQ; ++a) w[a] = g[f][a];
-#pragma unroll
-                                    for (int b = 0; b <= LQ; ++b) {
-#pragma unroll
-                                        for (int a = 0; a <= LP; ++a) u[b][a][f] = w[a];
-                                        if (b < LQ) {
-#pragma unroll
-                                            for (int a = 0; a < LPQ - b; ++a) w[a] = w[a + 1] + AB * w[a];
-                                        }
-                                    }
-                                }
-#pragma unroll
-                                for (int a = 0; a <= LP; ++a)
-#pragma unroll
-                                    for (int b = 0; b <= LQ; ++b) {
-                                        double v[LRS + 1];
-#pragma unroll
-                                        for (int f = 0; f <= LRS; ++f) v[f] = u[b][a][f];
-#pragma unroll
-                                        for (int d = 0; d <= LS; ++d) {
-#pragma unroll
-                                            for (int c = 0; c <= LR; ++c)
-                                                g4[axis][((a * (LQ + 1) + b) * (LR + 1) + c) * (LS + 1) + d] = v[c];
-                                            if (d < LS) {
-#pragma unroll
-                                                for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
-                                            }
-                                        }
-                                    }
-                            }
-#pragma unroll
-                            for (int a = 0; a < NFP; ++a)
-#pragma unroll
-                            for (int b = 0; b < NFQ; ++b)
-#pragma unroll
-                            for (int c = 0; c < NFR; ++c)
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) {
-                                gout[((a * NFQ + b) * NFR + c) * NFS + d] +=
-                                    g4[0][((cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * (LR + 1) + cart_x(LR, c)) * (LS + 1) + cart_x(LS, d)]
-                                  * g4[1][((cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * (LR + 1) + cart_y(LR, c)) * (LS + 1) + cart_y(LS, d)]
-                                  * g4[2][((cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * (LR + 1) + cart_z(LR, c)) * (LS + 1) + cart_z(LS, d)];
-                            }
-                        }
-                    }
+                    for (int irs = 0; irs < nrs; ++irs)
+                        jkt_prim_quartet<LP, LQ, LR, LS>(gout, zeta, Px, Py, Pz, cpq, Ax, Ay, Az, ABx, ABy, ABz,
+                                                         rsprim + irs * 5, Cx, Cy, Cz, CDx, CDy, CDz,
+                                                         t.omega, rys_tab);
                 }
 
                 // ---------------- digestion (thread-local) ----------------

@@ -51,6 +51,14 @@ def load_library(name='libgvhf_rys_b200'):
         vp, vp, vp, c_int, c_int, vp, vp,
         vp, vp, c_int, vp, vp, c_int,
         vp, c_float, c_float, c_float, c_int, c_int, c_int, vp, vp, vp, ctypes.c_double]
+    lib.B200_build_jk_rows.restype = c_int
+    lib.B200_build_jk_rows.argtypes = [
+        vp, vp, vp, vp, vp, c_int, c_int, vp, vp,
+        vp, vp, c_int,
+        vp, vp, vp, vp, vp, vp, c_int,
+        vp, c_float, c_float, c_int, c_int, c_int, vp, vp, ctypes.c_double]
+    lib.B200_has_row_class.restype = c_int
+    lib.B200_has_row_class.argtypes = [c_int, c_int, c_int, c_int]
     lib.B200_pair_rec_stride.restype = c_int
     lib.B200_pair_rec_stride.argtypes = [c_int, c_int]
     lib.B200_pair_records.restype = c_int

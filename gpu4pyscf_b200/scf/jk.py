@@ -6,15 +6,16 @@ Public surface kept from the reference (gpu4pyscf/scf/jk.py:60-230, 407-927):
 ``bas_pair_cache``, ``rys_envs``, ``h_shls``, ``coeff``, ``direct_scf_tol``.
 
 What is new underneath: host arrays are torch CUDA tensors (CuPy is not in the
-image; the C-ABI takes raw device pointers so it is array-library agnostic),
-the screening data are exactly q-sorted shell-pair lists per group pair, and one
-launch handles an unordered pair of group pairs {(gi,gj),(gk,gl)} -- which of the
-two is the register-tile side of the kernel is the library's choice
-(B200_has_class).  Multi-GPU: one process per GPU; every rank takes the work
-items (X pair, chunk of the q-sorted Y list) with ``item % world == rank`` of each
-launch (neighbouring items have near-equal cost, so the round-robin deal is
-balanced) and the partial ``[vj|vk]`` buffers are summed with ONE ``all_reduce``
-per build.
+image; the C-ABI takes raw device pointers so it is array-library agnostic).
+Every group pair carries two views of its significant shell pairs: a flat list
+sorted by the Schwarz bound q (the resident X side of a launch) and a ROW list
+grouped by one shell of the pair (the streamed Y side of the row-stream kernels:
+three shells of every quartet a warp evaluates are warp-uniform).  One launch
+handles an unordered pair of group pairs; which of the two is streamed, and
+through which kernel family, is decided per launch (``class_tasks``).
+Multi-GPU: one process per GPU; every rank takes the work items with
+``item % world == rank`` of each launch and the partial ``[vj|vk]`` buffer is
+summed with ONE ``all_reduce`` per build.
 """
 import ctypes
 import math
@@ -42,50 +43,79 @@ def _as_device_tensor(a, device):
     return torch.as_tensor(np.asarray(a, dtype=np.float64), device=device)
 
 
+def _check_rsh_factors(mol, omega, lr_factor, sr_factor):
+    '''(omega, lr_factor, sr_factor) of the exchange operator
+    lr_factor * erf(|omega| r)/r + sr_factor * erfc(|omega| r)/r, normalised exactly like
+    the reference (gpu4pyscf/scf/jk.py:1122-1168): omega < 0 flags that the short-range
+    part is needed, lr == sr collapses to omega = 0 with that factor.'''
+    if omega is None:
+        omega = mol.omega
+    if lr_factor is None and sr_factor is None:
+        if omega == 0:
+            lr_factor = sr_factor = 1
+        elif omega < 0:
+            lr_factor, sr_factor = 0, 1
+        else:
+            lr_factor, sr_factor = 1, 0
+    elif lr_factor is None:
+        lr_factor = sr_factor if omega == 0 else 0
+    elif sr_factor is None:
+        if omega == 0:
+            sr_factor = lr_factor
+        else:
+            assert omega > 0
+            sr_factor = 0
+    else:
+        if omega == 0:
+            assert lr_factor == sr_factor
+        elif lr_factor == sr_factor:
+            omega = 0
+    if sr_factor != 0 and omega != 0:
+        omega = -abs(omega)
+    return omega, lr_factor, sr_factor
+
+
+def _operator_terms(omega, lr_factor, sr_factor):
+    '''[(coefficient, w)] with w = 0 for 1/r and w > 0 for erf(w r)/r -- the two operators the
+    kernels evaluate (reference: rys_roots_for_k.cu:25-60).'''
+    if omega == 0:
+        terms = [(float(lr_factor), 0.)]
+    elif sr_factor == 0:
+        terms = [(float(lr_factor), abs(float(omega)))]
+    else:
+        terms = [(float(sr_factor), 0.), (float(lr_factor) - float(sr_factor), abs(float(omega)))]
+    return [(c, w) for c, w in terms if c != 0]
+
+
 def get_jk(mol, dm, hermi=0, vhfopt=None, with_j=True, with_k=True,
            omega=None, lr_factor=None, sr_factor=None, verbose=None):
     '''Coulomb (J) and exchange (K) matrices for one or several density
-    matrices; same contract as gpu4pyscf.scf.jk.get_jk (jk.py:60-151).
+    matrices; same contract as gpu4pyscf.scf.jk.get_jk (jk.py:60-151): omega, lr_factor and
+    sr_factor define the operator of K only; J always uses the molecule's own operator.
     Returns arrays shaped like ``dm`` living on the device.'''
     assert with_j or with_k
     if vhfopt is None:
         vhfopt = _VHFOpt(mol).build()
-    if omega is None:
-        omega = mol.omega
     dm = _as_device_tensor(dm, vhfopt.device)
     nao_orig = dm.shape[-1]
     dms = dm.reshape(-1, nao_orig, nao_orig)
     dms = vhfopt.apply_coeff_C_mat_CT(dms).contiguous()
-    # Range separation (reference: jk.py:1122-1168).  The kernels evaluate the full
-    # operator (omega = 0) or the long-range one erf(|omega| r)/r; everything else is
-    # a linear combination:  SR = full - LR,  lr_factor*LR + sr_factor*SR =
-    # sr_factor*full + (lr_factor - sr_factor)*LR.
-    if omega == 0 or omega is None:
-        c_full, c_lr = 1., 0.
-        if lr_factor is not None or sr_factor is not None:
-            raise ValueError('lr_factor/sr_factor need omega != 0')
-    elif lr_factor is None and sr_factor is None:
-        c_full, c_lr = (0., 1.) if omega > 0 else (1., -1.)
-    else:
-        lr = 0. if lr_factor is None else float(lr_factor)
-        sr = 0. if sr_factor is None else float(sr_factor)
-        c_full, c_lr = sr, lr - sr
+    omega, lr_factor, sr_factor = _check_rsh_factors(mol, omega, lr_factor, sr_factor)
     vj = vk = None
-    for coef, w in ((c_full, 0.), (c_lr, abs(float(omega or 0.)))):
-        if coef == 0:
-            continue
-        tj, tk = vhfopt.get_jk(dms, hermi, verbose, with_j=with_j, with_k=with_k, omega=w)
-        if tj is not None:
-            vj = coef * tj if vj is None else vj + coef * tj
-        if tk is not None:
-            vk = coef * tk if vk is None else vk + coef * tk
+    if omega == 0 and lr_factor == 1 and mol.omega == 0:
+        vj, vk = vhfopt._jk_pass(dms, hermi, with_j, with_k, 0.)
+    else:
+        if with_k:
+            vk = vhfopt.get_k(dms, hermi, verbose, omega, lr_factor, sr_factor)
+        if with_j:
+            vj = vhfopt.get_j(dms if hermi == 1 else (dms + dms.transpose(1, 2)) * .5, verbose)
     if with_k:
-        vk = vhfopt.apply_coeff_CT_mat_C(vk).reshape(dm.shape) if vk is not None else torch.zeros_like(dm)
+        vk = vhfopt.apply_coeff_CT_mat_C(vk).reshape(dm.shape)
+    else:
+        vk = None
     if with_j:
-        if vj is None:      # hermi == 2 (J of an anti-symmetric density vanishes) or zero coefficients
-            vj = torch.zeros_like(dm)
-        else:
-            vj = vhfopt.apply_coeff_CT_mat_C(vj).reshape(dm.shape)
+        # hermi == 2: J of an anti-symmetric density vanishes
+        vj = vhfopt.apply_coeff_CT_mat_C(vj).reshape(dm.shape) if vj is not None else torch.zeros_like(dm)
     else:
         vj = None
     return vj, vk
@@ -93,12 +123,30 @@ def get_jk(mol, dm, hermi=0, vhfopt=None, with_j=True, with_k=True,
 
 def get_k(mol, dm, hermi=0, vhfopt=None, omega=None, lr_factor=None, sr_factor=None, verbose=None):
     '''K only (reference: jk.py:153-204)'''
-    return get_jk(mol, dm, hermi, vhfopt, False, True, omega, lr_factor, sr_factor, verbose)[1]
+    if vhfopt is None:
+        vhfopt = _VHFOpt(mol).build()
+    dm = _as_device_tensor(dm, vhfopt.device)
+    nao_orig = dm.shape[-1]
+    dms = vhfopt.apply_coeff_C_mat_CT(dm.reshape(-1, nao_orig, nao_orig)).contiguous()
+    vk = vhfopt.get_k(dms, hermi, verbose, omega, lr_factor, sr_factor)
+    return vhfopt.apply_coeff_CT_mat_C(vk).reshape(dm.shape)
 
 
 def get_j(mol, dm, hermi=0, vhfopt=None, verbose=None):
     '''J only (reference: jk.py:206-230)'''
-    return get_jk(mol, dm, hermi, vhfopt, True, False, None, None, None, verbose)[0]
+    if vhfopt is None:
+        vhfopt = _VHFOpt(mol).build()
+    dm = _as_device_tensor(dm, vhfopt.device)
+    nao_orig = dm.shape[-1]
+    dms = vhfopt.apply_coeff_C_mat_CT(dm.reshape(-1, nao_orig, nao_orig)).contiguous()
+    if hermi != 1:
+        dms = (dms + dms.transpose(1, 2)) * .5
+    vj = vhfopt.get_j(dms, verbose)
+    return vhfopt.apply_coeff_CT_mat_C(vj).reshape(dm.shape)
+
+
+def _nf(l):
+    return (l + 1) * (l + 2) // 2
 
 
 class _VHFOpt:
@@ -120,9 +168,14 @@ class _VHFOpt:
         # reference's _TimingCollector (jk.py:1170-1188); costs a sync per class
         self.class_timing = None
         self.n_streams = int(os.environ.get('B200_STREAMS', '4'))
-        # width (log units) of the q bins of the pair lists; 0 = exactly q-sorted lists
+        # width (log units) of the q bins of the flat pair lists; 0 = exactly q-sorted lists
         self.q_bin = float(os.environ.get('B200_Q_BIN', '0.5'))
+        # row-stream kernels are used when the streamed list has rows at least this long on average
+        self.row_min = float(os.environ.get('B200_ROW_MIN', '12'))
         self._streams = None
+        self._tasks = None
+        self._qmax_cache = None
+        self._rows = {}
 
     def reset(self, mol):
         self.mol = mol
@@ -131,6 +184,7 @@ class _VHFOpt:
         self._rys_envs = None
         self._tasks = None
         self._qmax_cache = None
+        self._rows = {}
         return self
 
     # ------------------------------------------------------------------
@@ -149,6 +203,8 @@ class _VHFOpt:
         self._make_rys_envs()
         self.bas_pair_cache = _cache_q_cond_and_non0pairs(
             smol, self._rys_envs, self.direct_scf_tol, self.device, lib, self.q_bin)
+        self._rows = {}
+        self._tasks = None
         return self
 
     def _make_rys_envs(self):
@@ -183,54 +239,110 @@ class _VHFOpt:
         return 0, 1
 
     # ------------------------------------------------------------------
+    def row_list(self, key):
+        '''Row view of group pair ``key = (gi, gj)``: the pairs grouped by one shell p (the row
+        shell) with the partner q running over the row; q is the shell with the lower angular
+        momentum (for equal l: the one from the larger group, i.e. the longer rows).  Pair ids
+        are ``p*nbas+q`` in (p, q) = kernel order, records follow that order.'''
+        if key in self._rows:
+            return self._rows[key]
+        lib = loader.load_library()
+        smol = self.sorted_mol
+        nbas = smol.nbas
+        uniq = smol.uniq_l_ctr
+        counts = np.asarray(smol.l_ctr_counts)
+        gi, gj = key
+        ids, q = self.bas_pair_cache[key][:2]
+        li, lj = int(uniq[gi, 0]), int(uniq[gj, 0])
+        stream_second = li > lj or counts[gj] >= counts[gi]
+        gp, gq = (gi, gj) if stream_second else (gj, gi)
+        ish = torch.div(ids.to(torch.int64), nbas, rounding_mode='floor')
+        jsh = ids.to(torch.int64) - ish * nbas
+        p, qs = (ish, jsh) if stream_second else (jsh, ish)
+        order = torch.argsort(p * nbas + qs)
+        p, qs, qv = p[order], qs[order], q[order].contiguous()
+        pair = (p * nbas + qs).to(torch.int32).contiguous()
+        if len(pair):
+            row_p, cnt = torch.unique_consecutive(p, return_counts=True)
+            row_ptr = torch.zeros(len(row_p) + 1, dtype=torch.int32, device=ids.device)
+            row_ptr[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+            row_qmax = torch.segment_reduce(qv, 'max', lengths=cnt).contiguous()
+            row_p = row_p.to(torch.int32).contiguous()
+        else:
+            row_p = torch.zeros(0, dtype=torch.int32, device=ids.device)
+            row_ptr = torch.zeros(1, dtype=torch.int32, device=ids.device)
+            row_qmax = torch.zeros(0, dtype=torch.float32, device=ids.device)
+        npp, npq = int(uniq[gp, 1]), int(uniq[gq, 1])
+        rec = torch.empty(max(1, len(pair) * lib.B200_pair_rec_stride(npp, npq)), dtype=torch.float64,
+                          device=ids.device)
+        if len(pair):
+            err = lib.B200_pair_records(_ptr(rec), ctypes.byref(self._rys_envs), _ptr(pair), len(pair), npp, npq,
+                                        loader.current_stream_ptr())
+            if err:
+                raise RuntimeError('B200_pair_records failed')
+        out = dict(pair=pair, q=qv, rec=rec, row_ptr=row_ptr, row_p=row_p, row_qmax=row_qmax,
+                   nrows=len(row_p), mean_len=len(pair) / max(1, len(row_p)),
+                   lp=int(uniq[gp, 0]), lq=int(uniq[gq, 0]), nprim_p=npp, nprim_q=npq)
+        self._rows[key] = out
+        return out
+
     def class_tasks(self):
-        '''Launch list: (group pair Y, group pair X, dedupe) for every unordered
-        pair of group pairs.  Y is the lane side and X the register-tile side of
-        the kernel; the library says which orientation of a class it instantiates.'''
-        if getattr(self, '_tasks', None) is not None:
+        '''Launch list: one entry per unordered pair of group pairs:
+        ``('flat', Y key, X key, dedupe)`` -- both lists flat and q-sorted (rys_jk_thread /
+        rys_jk_warp kernels), or ``('row', Y key, X key, dedupe)`` -- Y streamed through its row
+        view.  Y is the lane side and X the resident side of the kernel.'''
+        if self._tasks is not None:
             return self._tasks
         lib = loader.load_library()
         smol = self.sorted_mol
         uniq = smol.uniq_l_ctr
         keys = sorted(self.bas_pair_cache.keys())
+        use_rows = os.environ.get('B200_ROWS', '1') == '1'
 
         def ls(key):
             return int(uniq[key[0], 0]), int(uniq[key[1], 0])
 
+        def row_score(ky, kx):
+            '''cost estimate of streaming ky through its row view against resident kx (lower is
+            better), or None when no row-stream kernel exists / rows are too short'''
+            if not use_rows or len(self.bas_pair_cache[ky][0]) == 0:
+                return None
+            rl = self.row_list(ky)
+            if rl['mean_len'] < self.row_min:
+                return None
+            lr, ls_ = ls(kx)
+            if not lib.B200_has_row_class(rl['lp'], rl['lq'], lr, ls_):
+                return None
+            scattered = _nf(rl['lq']) * (_nf(rl['lp']) + _nf(lr) + _nf(ls_))
+            return scattered * (1. + 16. / rl['mean_len'])
+
         tasks = []
         for ia, ka in enumerate(keys):
             for kb in keys[:ia + 1]:
-                if ka == kb:
-                    tasks.append((ka, ka, 1))
+                cands = [(ka, kb)] if ka == kb else [(ka, kb), (kb, ka)]
+                best = None
+                for ky, kx in cands:
+                    sc = row_score(ky, kx)
+                    if sc is not None and (best is None or sc < best[0]):
+                        best = (sc, ky, kx)
+                if best is not None:
+                    tasks.append(('row', best[1], best[2], 1 if ka == kb else 0))
+                elif ka == kb:
+                    tasks.append(('flat', ka, ka, 1))
                 elif lib.B200_has_class(*ls(kb), *ls(ka)):
-                    tasks.append((kb, ka, 0))      # (Y, X)
+                    tasks.append(('flat', kb, ka, 0))      # (Y, X)
                 else:
-                    tasks.append((ka, kb, 0))
-        # optional longest-processing-time order; measured slower than the natural group order on
-        # Taxol (6.77 s vs 6.63 s), so it is off by default
-        if os.environ.get('B200_SORT_TASKS', '0') == '1':
-            from . import flops
-
-            def cost(task):
-                ky, kx, _ = task
-                lprim = tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 0]) + \
-                    tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 1])
-                return len(self.bas_pair_cache[ky][0]) * len(self.bas_pair_cache[kx][0]) * flops.f_quartet(lprim)
-            tasks.sort(key=cost, reverse=True)
-        mode = os.environ.get('B200_SORT_TASKS', '0')
-        if mode == '2':
-            tasks.reverse()
-        elif mode == '3':       # launches of the same kernel instantiation next to each other
-            tasks.sort(key=lambda tk: ls(tk[0]) + ls(tk[1]))
+                    tasks.append(('flat', ka, kb, 0))
         self._tasks = tasks
         return tasks
 
-    def get_jk(self, dms, hermi=0, verbose=None, with_j=True, with_k=True, omega=0.):
-        '''J/K in the sorted Cartesian basis.  dms: (n_dm, nao, nao) device
-        tensor.  Returns (vj, vk) (None where not requested).  omega = 0: 1/r,
-        omega > 0: long-range erf(omega r)/r.'''
-        if omega < 0:
-            raise ValueError('short range is composed by the caller as full - long range')
+    # ------------------------------------------------------------------
+    def _jk_pass(self, dms, hermi, with_j, with_k, omega):
+        '''One pass over all quartets with the operator 1/r (omega = 0) or erf(omega r)/r
+        (omega > 0): J/K in the sorted Cartesian basis, symmetrised as the reference does
+        (jk.py:594-616).  dms: (n_dm, nao, nao) device tensor.  Returns (vj, vk), None where not
+        requested.'''
+        assert omega >= 0
         lib = loader.load_library()
         smol = self.sorted_mol
         dev = self.device
@@ -246,8 +358,30 @@ class _VHFOpt:
         ndm_k = dms.shape[0]
         if hermi == 2:
             with_j = False
+        if not (with_j or with_k):
+            return None, None
         envs = self._rys_envs
         stream = loader.current_stream_ptr()
+        tasks = self.class_tasks()
+        any_rows = any(tk[0] == 'row' for tk in tasks)
+        # transposed views for the row-stream kernels: dmT[k] = dms[k]^T; K blocks written through
+        # vkT[k] are added back transposed.  Symmetric D: both alias the originals.
+        if hermi == 1 or not any_rows:
+            dmT = dms
+        elif hermi == 0:
+            dmT = torch.cat([dms[n_dm:], dms[:n_dm]], dim=0).contiguous()
+        else:
+            dmT = -dms
+        sep_kT = with_k and any_rows and hermi != 1
+        # one contiguous output buffer [vj | vk | vkT]: a single all_reduce, no concatenation
+        nj = ndm_k if with_j else 0
+        nk = ndm_k if with_k else 0
+        nt = ndm_k if sep_kT else 0
+        out = torch.zeros((nj + nk + nt, nao, nao), dtype=torch.float64, device=dev)
+        vj = out[:nj] if with_j else None
+        vk = out[nj:nj + nk] if with_k else None
+        vkT = out[nj + nk:] if sep_kT else vk
+
         # Class launches are independent (they only meet in the J/K atomics), so
         # they are dealt over a few side streams: the tail of one launch, when
         # most SMs have run out of work items, overlaps the start of the next.
@@ -265,12 +399,9 @@ class _VHFOpt:
         dm_penalty = float(dm_cond.max())
         cutoff = math.log(self.direct_scf_tol)
 
-        vj = torch.zeros_like(dms) if with_j else None
-        vk = torch.zeros_like(dms) if with_k else None
-        tasks = self.class_tasks()
         if getattr(self, 'counter', None) is not None:
             self._counter_last = int(self.counter.item())
-        heads = torch.zeros(len(tasks) + 1, dtype=torch.int32, device=dev)
+        heads = torch.zeros(len(tasks) + 1, dtype=torch.int64, device=dev)
         if side is not None:
             ev = torch.cuda.Event()
             ev.record(main)
@@ -280,45 +411,56 @@ class _VHFOpt:
         uniq = smol.uniq_l_ctr
         lprim = (ctypes.c_int * 8)()
         only = getattr(self, 'only_classes', None)   # measurement: restrict to some classes
-        for it, (ky, kx, dedupe) in enumerate(tasks):
-            if only is not None:
-                l4 = tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 0])
-                p4 = tuple(int(v) for v in uniq[[ky[0], ky[1], kx[0], kx[1]], 1])
-                if l4 not in only and l4 + p4 not in only:
-                    continue
+        for it, (mode, ky, kx, dedupe) in enumerate(tasks):
             pair_x, q_x = self.bas_pair_cache[kx][:2]
-            pair_y, q_y = self.bas_pair_cache[ky][:2]
-            rec_y = self.bas_pair_cache[ky][3]
-            if len(pair_x) == 0 or len(pair_y) == 0:
+            if len(pair_x) == 0 or len(self.bas_pair_cache[ky][0]) == 0:
                 continue
             # cheap class-level early exit
             if float(self._qmax[kx]) + float(self._qmax[ky]) + dm_penalty < cutoff:
                 continue
-            lprim[0], lprim[1] = int(uniq[ky[0], 0]), int(uniq[ky[1], 0])
             lprim[2], lprim[3] = int(uniq[kx[0], 0]), int(uniq[kx[1], 0])
-            lprim[4], lprim[5] = int(uniq[ky[0], 1]), int(uniq[ky[1], 1])
             lprim[6], lprim[7] = int(uniq[kx[0], 1]), int(uniq[kx[1], 1])
-            head = ctypes.c_void_p(heads.data_ptr() + 4 * it)
+            if mode == 'row':
+                rl = self.row_list(ky)
+                lprim[0], lprim[1], lprim[4], lprim[5] = rl['lp'], rl['lq'], rl['nprim_p'], rl['nprim_q']
+            else:
+                lprim[0], lprim[1] = int(uniq[ky[0], 0]), int(uniq[ky[1], 0])
+                lprim[4], lprim[5] = int(uniq[ky[0], 1]), int(uniq[ky[1], 1])
+            if only is not None:
+                if tuple(lprim[:4]) not in only and tuple(lprim) not in only:
+                    continue
+            head = ctypes.c_void_p(heads.data_ptr() + 8 * it)
             if self.class_timing is not None and dev.type == 'cuda':
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
             if side is not None:
                 stream = ctypes.c_void_p(side[it % len(side)].cuda_stream)
-            err = lib.B200_build_jk_class(
-                _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
-                _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
-                _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, rank, world, head, stream, _ptr(rec_y), float(omega))
+            if mode == 'row':
+                err = lib.B200_build_jk_rows(
+                    _ptr(vj), _ptr(vk), _ptr(vkT), _ptr(dms), _ptr(dmT), ndm_k, nao, ctypes.byref(envs), lprim,
+                    _ptr(pair_x), _ptr(q_x), len(pair_x),
+                    _ptr(rl['pair']), _ptr(rl['q']), _ptr(rl['rec']),
+                    _ptr(rl['row_ptr']), _ptr(rl['row_p']), _ptr(rl['row_qmax']), rl['nrows'],
+                    _ptr(dm_cond), cutoff, dm_penalty, dedupe, rank, world, head, stream, float(omega))
+            else:
+                pair_y, q_y = self.bas_pair_cache[ky][:2]
+                rec_y = self.bas_pair_cache[ky][3]
+                err = lib.B200_build_jk_class(
+                    _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
+                    _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
+                    _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, rank, world, head, stream,
+                    _ptr(rec_y), float(omega))
             if err:
-                raise RuntimeError('B200_build_jk_class failed for class %s' % (tuple(lprim),))
+                raise RuntimeError('J/K launch failed for class %s (%s)' % (tuple(lprim), mode))
             if self.class_timing is not None and dev.type == 'cuda':
                 ev1.record()
                 ev1.synchronize()
-                key = tuple(lprim)
+                key = tuple(lprim) + (mode,)
                 rec = self.class_timing.setdefault(key, [0., 0, 0, 0])
                 rec[0] += ev0.elapsed_time(ev1)
                 rec[1] += len(pair_x)
-                rec[2] += len(pair_y)
+                rec[2] += len(self.bas_pair_cache[ky][0])
                 if getattr(self, 'counter', None) is not None:
                     n = int(self.counter.item())
                     rec[3] += n - self._counter_last
@@ -331,17 +473,12 @@ class _VHFOpt:
                 main.wait_event(ev)
 
         if world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
-            # one collective per build over the concatenated [vj|vk] partials
-            bufs = [b for b in (vj, vk) if b is not None]
-            flat = torch.cat([b.reshape(-1) for b in bufs])
-            torch.distributed.all_reduce(flat)
-            off = 0
-            for b in bufs:
-                b.copy_(flat[off:off + b.numel()].reshape(b.shape))
-                off += b.numel()
+            torch.distributed.all_reduce(out)       # one collective per build over [vj|vk|vkT]
 
         # symmetrisation of the partial sums (reference: jk.py:594-616)
         if with_k:
+            if sep_kT:
+                vk = vk + vkT.transpose(1, 2)
             if hermi == 1:
                 vk = vk + vk.transpose(1, 2)
             elif hermi == 2:
@@ -356,25 +493,45 @@ class _VHFOpt:
             vj = vj + vj.transpose(1, 2)
         return vj, vk
 
+    def _combine(self, dms, hermi, with_j, with_k, terms):
+        '''sum of coefficient * pass over the operator terms [(coef, w)]'''
+        vj = vk = None
+        for coef, w in terms:
+            tj, tk = self._jk_pass(dms, hermi, with_j, with_k, w)
+            if tj is not None:
+                tj = tj if coef == 1 else tj * coef
+                vj = tj if vj is None else vj + tj
+            if tk is not None:
+                tk = tk if coef == 1 else tk * coef
+                vk = tk if vk is None else vk + tk
+        return vj, vk
+
+    def _own_terms(self):
+        '''operator of the molecule itself (mol.omega, libcint sign convention)'''
+        return _operator_terms(*_check_rsh_factors(self.mol, None, None, None))
+
+    def get_jk(self, dms, hermi=0, verbose=None, with_j=True, with_k=True):
+        '''J and K in the sorted Cartesian basis with the molecule's own Coulomb operator
+        (reference: _VHFOpt.get_jk, jk.py:492-641, which reads omega from the sorted mol's env).'''
+        dms = dms.reshape(-1, self.sorted_mol.nao, self.sorted_mol.nao)
+        vj, vk = self._combine(dms, hermi, with_j, with_k, self._own_terms())
+        if with_j and vj is None:
+            vj = torch.zeros_like(dms)
+        if with_k and vk is None:
+            vk = torch.zeros_like(dms)
+        return vj, vk
+
     def get_j(self, dms, verbose=None):
+        '''J of symmetric density matrices (reference: jk.py:643-783)'''
         return self.get_jk(dms, 1, verbose, with_j=True, with_k=False)[0]
 
-    def get_k(self, dms, hermi=0, verbose=None, omega=0, lr_factor=None, sr_factor=None):
-        if not omega:
-            return self.get_jk(dms, hermi, verbose, with_j=False, with_k=True)[1]
-        if lr_factor is None and sr_factor is None:
-            c_full, c_lr = (0., 1.) if omega > 0 else (1., -1.)
-        else:
-            lr = 0. if lr_factor is None else float(lr_factor)
-            sr = 0. if sr_factor is None else float(sr_factor)
-            c_full, c_lr = sr, lr - sr
-        vk = None
-        for coef, w in ((c_full, 0.), (c_lr, abs(float(omega)))):
-            if coef == 0:
-                continue
-            tk = self.get_jk(dms, hermi, verbose, with_j=False, with_k=True, omega=w)[1]
-            vk = coef * tk if vk is None else vk + coef * tk
-        return vk
+    def get_k(self, dms, hermi=0, verbose=None, omega=None, lr_factor=None, sr_factor=None):
+        '''K with the operator lr_factor*erf(|omega| r)/r + sr_factor*erfc(|omega| r)/r (reference:
+        jk.py:785-927; omega = None: the molecule's own operator)'''
+        dms = dms.reshape(-1, self.sorted_mol.nao, self.sorted_mol.nao)
+        terms = _operator_terms(*_check_rsh_factors(self.mol, omega, lr_factor, sr_factor))
+        vk = self._combine(dms, hermi, False, True, terms)[1]
+        return vk if vk is not None else torch.zeros_like(dms)
 
     @property
     def _qmax(self):
@@ -424,7 +581,8 @@ def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib, q_bin=0.
             # neighbours in the list share the bra shell, so the D rows they load and the
             # K rows they update coincide (the kernels get q_margin = q_bin for the early exit)
             bins = torch.floor(q.double() / q_bin).to(torch.int64)
-            order = torch.argsort((bins.max() - bins) * (int(nbas) * int(nbas)) + ids.to(torch.int64))
+            order = torch.argsort((bins.max() - bins) * (int(nbas) * int(nbas)) + ids.to(torch.int64)) \
+                if len(q) else torch.zeros(0, dtype=torch.int64, device=device)
         else:
             order = torch.argsort(q, descending=True, stable=True)
         ids = ids[order].contiguous()

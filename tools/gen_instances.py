@@ -139,6 +139,29 @@ def cost(c):
     return nf(lp) * nf(lq) * nf(lr) * nf(ls)
 
 
+# ---- row-stream kernels: Y = (p,q) rows of a uniform shell p, q streamed over lanes ----
+ROWT_MAX_NF = int(os.environ.get('B200_ROWT_MAX_NF', '54'))        # integrals per lane
+ROWT_MAX_LIVE = int(os.environ.get('B200_ROWT_MAX_LIVE', '100'))   # + row/item accumulators (doubles)
+
+
+def rowt_ok(lp, lq, lr, ls, ndm):
+    n = nf(lp) * nf(lq) * nf(lr) * nf(ls)
+    acc = ndm * (nf(lp) * (nf(lr) + nf(ls)) + nf(lr) * nf(ls))
+    return n <= ROWT_MAX_NF and n + acc <= ROWT_MAX_LIVE
+
+
+def row_classes():
+    """(lp, lq, lr, ls, kind) with lp >= lq (q = streamed shell), lr >= ls; every orientation
+    that fits is instantiated, the host picks per launch."""
+    types = [(a, b) for a in range(LMAX + 1) for b in range(a + 1)]
+    out = []
+    for y in types:
+        for x in types:
+            if rowt_ok(y[0], y[1], x[0], x[1], 1):
+                out.append((y[0], y[1], x[0], x[1], 't'))
+    return out
+
+
 def main(dst):
     os.makedirs(dst, exist_ok=True)
     cls = sorted(classes(), key=cost, reverse=True)
@@ -189,8 +212,28 @@ def main(dst):
                             '{ return jk_launch<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
                             % (name, lp, lq, lr, ls, ncs, ndm))
                     decls.append((lp, lq, lr, ls, ndm, name))
+    # row-stream instantiations, dealt over the same units
+    rdecls = []
+    rcls = sorted(row_classes(), key=lambda c: cost(c[:4]), reverse=True)
+    for n, (lp, lq, lr, ls, kind) in enumerate(rcls):
+        with open(os.path.join(dst, 'jk_inst_%02d.cu' % (n % NUNITS)), 'a') as f:
+            for ndm in (1, 2):
+                if kind == 't' and not rowt_ok(lp, lq, lr, ls, ndm):
+                    continue
+                name = 'jk_launch_row_%d%d%d%d_%d' % (lp, lq, lr, ls, ndm)
+                f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
+                        '{ return jk_launch_rowt<%d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
+                        % (name, lp, lq, lr, ls, ndm))
+                rdecls.append((lp, lq, lr, ls, ndm, name))
     with open(os.path.join(dst, 'jk_dispatch.inc'), 'w') as f:
         f.write('// GENERATED by tools/gen_instances.py\n')
+        for d in rdecls:
+            f.write('int %s(JKTask *, int, int, cudaStream_t);\n' % d[5])
+        f.write('static jk_launcher_t jk_find_row_launcher(int lp, int lq, int lr, int ls, int ndm)\n{\n'
+                '    switch ((((lp * 8 + lq) * 8 + lr) * 8 + ls) * 4 + ndm) {\n')
+        for (lp, lq, lr, ls, ndm, name) in rdecls:
+            f.write('    case %d: return %s;\n' % ((((lp * 8 + lq) * 8 + lr) * 8 + ls) * 4 + ndm, name))
+        f.write('    }\n    return nullptr;\n}\n')
         for d in decls:
             f.write('int %s(JKTask *, int, int, cudaStream_t);\n' % d[5])
         f.write('static jk_launcher_t jk_find_launcher(int lp, int lq, int lr, int ls, int ndm)\n{\n'
