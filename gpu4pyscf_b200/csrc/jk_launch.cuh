@@ -93,8 +93,23 @@ int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     return rt_last_error("rys_jk_thread_kernel");
 }
 
+// Work items of a row-stream launch: (X pair, block of consecutive rows).  Enough items for
+// `workers` independent warps/teams, few enough that the per-item X setup and the J_rs flush
+// stay amortised.
+static inline long long jk_set_rowblocks(JKTask *t, int workers)
+{
+    int rpi = 16;
+    static const char *force = getenv("B200_ROWS_PER_ITEM");   // tests: exercise the block logic on tiny inputs
+    if (force != nullptr && atoi(force) > 0) rpi = atoi(force);
+    else while (rpi > 1 && (long long)t->npair_x * ((t->nrows + rpi - 1) / rpi) < 16LL * workers * t->world) rpi >>= 1;
+    t->rows_per_item = rpi;
+    t->nrowblk = (t->nrows + rpi - 1) / rpi;
+    long long items = (long long)t->npair_x * t->nrowblk;
+    return (items + t->world - 1) / t->world;
+}
+
 // warp-team kernel (mid and high classes)
-template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0>
+template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0, int ROW = 0>
 int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
 {
     typedef JKWCfg<LP, LQ, LR, LS, NCS, BL> C;
@@ -121,9 +136,10 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     if (K < 1) K = 1;
     if (nprimq > 1 && K > nprimq) K = nprimq;
     const int minb = jkw_minblocks(C::TILE, NDM, NCS == 1 ? C::SUBSIZE : LS + 1, C::TEAM);
+    const int rowd = ROW ? 2 * NDM * C::NFP * (C::NFR + C::NFS) : 0;
     auto smem_of = [&](int k) {
         return (RysSmem<C::NROOTS>::DOUBLES
-                + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET)) * 8;
+                + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET, rowd)) * 8;
     };
     const int budget = (smem_max + 1024) / minb - 1024;
     while (K > 1 && smem_of(K) > budget) --K;
@@ -135,34 +151,19 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         return 1;
     }
     t->nq = K;
-    t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET);
-    int per_sm = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL>, smem, nt);
+    t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET, rowd);
+    int per_sm = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL, ROW>, smem, nt);
     if (per_sm < 1) {
         fprintf(stderr, "rys_jk_warp: class (%d%d|%d%d) cannot be made resident (smem %d, threads %d)\n",
                 LP, LQ, LR, LS, smem, nt);
         return 1;
     }
     int grid = nsm * per_sm;
-    int nitems = jk_set_chunks(t, grid * nteams);
-    if (grid * nteams > nitems) grid = (nitems + nteams - 1) / nteams;
+    long long nitems = ROW ? jk_set_rowblocks(t, grid * nteams) : jk_set_chunks(t, grid * nteams);
+    if ((long long)grid * nteams > nitems) grid = (int)((nitems + nteams - 1) / nteams);
     if (grid < 1) return 0;
-    KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL>), grid, nt, smem, stream, *t);
+    KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL, ROW>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_warp_kernel");
-}
-
-// Work items of a row-stream launch: (X pair, block of consecutive rows).  Enough items for
-// `workers` independent warps/teams, few enough that the per-item X setup and the J_rs flush
-// stay amortised.
-static inline long long jk_set_rowblocks(JKTask *t, int workers)
-{
-    int rpi = 16;
-    static const char *force = getenv("B200_ROWS_PER_ITEM");   // tests: exercise the block logic on tiny inputs
-    if (force != nullptr && atoi(force) > 0) rpi = atoi(force);
-    else while (rpi > 1 && (long long)t->npair_x * ((t->nrows + rpi - 1) / rpi) < 16LL * workers * t->world) rpi >>= 1;
-    t->rows_per_item = rpi;
-    t->nrowblk = (t->nrows + rpi - 1) / rpi;
-    long long items = (long long)t->npair_x * t->nrowblk;
-    return (items + t->world - 1) / t->world;
 }
 
 // thread-per-quartet row-stream kernel (light classes)

@@ -27,17 +27,22 @@
 
 #define JKR_RED_ROWS 8          // values reduced per round of the shared-memory tree
 #define JKR_RED_STRIDE 33
+#define JKR_SCREEN 4            // candidates screened per lane and pass (independent loads in flight)
+#define JKR_QCAP (32 + 32 * JKR_SCREEN)   // survivor queue entries of a warp
 
 // shared-memory doubles of one warp: X primitive pairs, D_rs, D_p*, 64-entry queue, reduction scratch
 __host__ __device__ inline int jkrt_warp_doubles(int nrs, int ndm, int nfrs, int nfp, int nfr, int nfs)
 {
-    return (nrs * 5 + ndm * nfrs + ndm * nfp * (nfr + nfs) + 32 + JKR_RED_ROWS * JKR_RED_STRIDE + 1) & ~1;
+    return (nrs * 5 + ndm * nfrs + ndm * nfp * (nfr + nfs) + JKR_QCAP / 2 + JKR_RED_ROWS * JKR_RED_STRIDE + 1) & ~1;
 }
 
 __host__ __device__ constexpr int jkrt_minblocks(int nf_total, int nacc)
 {
+#ifdef JKRT_MINBLOCKS_FIXED
+    return JKRT_MINBLOCKS_FIXED;
+#endif
     // registers ~ 2 * (integrals + accumulators) + ~70 of addressing / recurrence state
-    return nf_total + nacc <= 4 ? 5 : (nf_total + nacc <= 12 ? 4 : (nf_total + nacc <= 30 ? 3 : 2));
+    return nf_total + nacc <= 4 ? 5 : (nf_total + nacc <= 12 ? 4 : (nf_total + nacc <= 48 ? 3 : 2));
 }
 
 // Sum `v[0..N)` of every lane over the warp and hand the N totals to `sink(i, total)`
@@ -99,8 +104,8 @@ rys_jk_rowt_kernel(JKTask t)
     double *rsprim = wsm;                            // nrs * 5: eta, Qx, Qy, Qz, coef
     double *drs = rsprim + nrs * 5;                  // NDM * NFRS
     double *dpx = drs + NDM * NFRS;                  // NDM * NFP * (NFR + NFS): D_pr | D_ps
-    uint32_t *queue = (uint32_t *)(dpx + NDM * NKP); // 64 entries
-    double *red = dpx + NDM * NKP + 32;
+    uint32_t *queue = (uint32_t *)(dpx + NDM * NKP); // JKR_QCAP entries
+    double *red = dpx + NDM * NKP + JKR_QCAP / 2;
     rys_stage_tables<NROOTS>(rys_tab, t.rys_cheb, t.rys_large, tid, blockDim.x);
     __syncthreads();
 
@@ -197,34 +202,53 @@ rys_jk_rowt_kernel(JKTask t)
             for (int n = 0; n < NDM * NKP; ++n) kacc[n] = 0.;
             int ypos = t.row_ptr[row];
             const int y_end = t.row_ptr[row + 1];
-            int qn = 0;
+            int qn = 0, qh = 0;                      // survivors queue[qh, qh + qn)
             bool exhausted = false;
             __syncwarp();
 
             while (true) {
                 // ---------------- screen partners q of p into the warp's queue ----------------
+                // JKR_SCREEN candidates per lane and pass: the dependent loads (pair id -> density
+                // bounds of q) of all of them are in flight together
+                if (!exhausted && qn < 32 && qh > 0) {      // fewer than 32 left: move them to the front
+                    uint32_t keepv = 0;
+                    if (lane < qn) keepv = queue[qh + lane];
+                    __syncwarp();
+                    if (lane < qn) queue[lane] = keepv;
+                    qh = 0;
+                    __syncwarp();
+                }
                 while (!exhausted && qn < 32) {
-                    const int y = ypos + lane;
-                    bool keep = false;
-                    if (y < y_end) {
-                        const float qy = t.q_y[y];
-                        keep = qy + t.dm_penalty >= thr;
-                        if (keep) {
-                            const int qsh = t.pair_y[y] - (uint32_t)psh * nbas;
-                            if (t.dedupe) {
-                                const uint32_t canon = psh >= qsh ? (uint32_t)psh * nbas + qsh : (uint32_t)qsh * nbas + psh;
-                                keep = canon >= pair_rs;
-                            }
-                            float dmax = d_uni;
-                            if (do_j) dmax = fmaxf(dmax, dc_p[qsh]);
-                            if (do_k) dmax = fmaxf(dmax, fmaxf(dc_r[qsh], dc_s[qsh]));
-                            keep = keep && (dmax + qy > thr);
-                        }
+                    float qy[JKR_SCREEN];
+                    int qsh[JKR_SCREEN];
+#pragma unroll
+                    for (int k = 0; k < JKR_SCREEN; ++k) {
+                        const int y = ypos + k * 32 + lane;
+                        const bool in = y < y_end;
+                        qy[k] = in ? t.q_y[y] : -1e30f;
+                        qsh[k] = in ? (int)(t.pair_y[y] - (uint32_t)psh * nbas) : psh;
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (keep) queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint32_t)y;
-                    qn += __popc(m);
-                    ypos += 32;
+                    float dq[JKR_SCREEN];
+#pragma unroll
+                    for (int k = 0; k < JKR_SCREEN; ++k) {
+                        float dmax = d_uni;
+                        if (do_j) dmax = fmaxf(dmax, dc_p[qsh[k]]);
+                        if (do_k) dmax = fmaxf(dmax, fmaxf(dc_r[qsh[k]], dc_s[qsh[k]]));
+                        dq[k] = dmax;
+                    }
+#pragma unroll
+                    for (int k = 0; k < JKR_SCREEN; ++k) {
+                        bool keep = qy[k] + t.dm_penalty >= thr && dq[k] + qy[k] > thr;
+                        if (t.dedupe) {
+                            const uint32_t canon = psh >= qsh[k] ? (uint32_t)psh * nbas + qsh[k]
+                                                                 : (uint32_t)qsh[k] * nbas + psh;
+                            keep = keep && canon >= pair_rs;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        if (keep) queue[qn + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(ypos + k * 32 + lane);
+                        qn += __popc(m);
+                    }
+                    ypos += 32 * JKR_SCREEN;
                     exhausted = ypos >= y_end;
                     __syncwarp();
                 }
@@ -232,7 +256,7 @@ rys_jk_rowt_kernel(JKTask t)
                 const int nb = qn < 32 ? qn : 32;
 
                 if (lane < nb) {
-                    const int iy = queue[lane];
+                    const int iy = queue[qh + lane];
                     const double *rec = t.rec_y + (size_t)iy * t.rec_stride;
                     const double2 h0 = *(const double2 *)(rec + 0);
                     const double2 h1 = *(const double2 *)(rec + 2);
@@ -320,16 +344,10 @@ rys_jk_rowt_kernel(JKTask t)
                     }
                 }   // lane < nb
 
-                // ---------------- keep the unprocessed remainder of the queue ----------------
                 __syncwarp();
                 if (lane == 0 && t.counter != nullptr) atomicAdd(t.counter, (unsigned long long)nb);
-                const int rem = qn - nb;
-                uint32_t keepv = 0;
-                if (lane < rem) keepv = queue[nb + lane];
-                __syncwarp();
-                if (lane < rem) queue[lane] = keepv;
-                qn = rem;
-                __syncwarp();
+                qh += nb;
+                qn -= nb;
                 if (exhausted && qn == 0) break;
             }
 

@@ -62,13 +62,14 @@ struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
 #define JKW_SLOT_HDR 8       // AB[3], A[3], fac, (p0,q0)
 
 // shared-memory doubles of one team (used by the kernel and by the launcher)
+// rowd: doubles of the row buffers of the row-stream variant (D_p* block + K_p* accumulators), else 0
 __host__ __device__ inline int jkw_team_doubles(int team_threads, int nsw, int K, int npq, int nrs,
-                                                int ndm, int nfrs, int gset)
+                                                int ndm, int nfrs, int gset, int rowd = 0)
 {
     int ngs = nsw * K;
     int nqs = (npq * nrs == 1) ? ngs : nsw;
     int qcap = nqs + team_threads;
-    int n = 8 + nrs * 5 + ndm * nfrs + (qcap + 1) / 2 + nqs * (JKW_SLOT_HDR + 5 * npq);
+    int n = 8 + nrs * 5 + ndm * nfrs + rowd + (qcap + 1) / 2 + nqs * (JKW_SLOT_HDR + 5 * npq);
     n = (n + 1) & ~1;                    // g-sets start 16-byte aligned
     return n + ngs * gset;
 }
@@ -134,7 +135,12 @@ __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int 
     return nb < 1 ? 1 : nb;
 }
 
-template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0>
+// ROW = 1: row-stream variant.  The Y list is grouped in rows of one shell p (JKTask::row_ptr /
+// row_p); a team owns (X pair, block of rows) and walks the rows one at a time, so p, r, s are
+// team-uniform: D_pr / D_ps are staged in shared memory once per row, K_pr / K_ps accumulate in
+// registers over the row and leave the team through a shared-memory panel at the row end, and
+// the q-dependent blocks are addressed with q as the column index (dmT / vkT), see rys_jk_rowt.cuh.
+template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0, int ROW = 0>
 __global__ void
 __launch_bounds__(jkw_block_threads(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM,
                                     JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE * (1 + NDM)),
@@ -145,6 +151,7 @@ rys_jk_warp_kernel(JKTask t)
 {
     typedef JKWCfg<LP, LQ, LR, LS, NCS, BL> C;
     constexpr int NBL = C::NBL;
+    constexpr int NBLANE = BL ? 1 : C::NFQ;                // q components spread over lanes
     constexpr int NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS, NFRS = C::NFRS;
     constexpr int LPQ = C::LPQ, LRS = C::LRS, NROOTS = C::NROOTS;
     constexpr int NC = C::NC, G = C::G;
@@ -177,13 +184,17 @@ rys_jk_warp_kernel(JKTask t)
     const int npass = single ? 1 : (nprimq + K - 1) / K;
 
     double *tm = smem + RysSmem<NROOTS>::DOUBLES + team * t.slot_doubles;
-    int *tm_ints = (int *)tm;                // [0] ix, [1] qn, [2] exhausted
+    int *tm_ints = (int *)tm;                // [0..1] work item (64 bit when ROW), [2] qn, [3] exhausted
     double *rsgeom = tm + 2;                 // CD[3], C[3]
     double *rsprim = tm + 8;                 // nrs * 5: eta, Qx, Qy, Qz, coef
     double *drs = rsprim + nrs * 5;
-    uint32_t *queue = (uint32_t *)(drs + NDM * NFRS);
-    double *slots = drs + NDM * NFRS + (qcap + 1) / 2;
-    double *gsets = tm + ((8 + nrs * 5 + NDM * NFRS + (qcap + 1) / 2 + nqs * slot_d + 1) & ~1);
+    constexpr int NKP = C::NFP * (NFR + NFS);              // K_pr | K_ps values of one density matrix
+    constexpr int ROWD = ROW ? 2 * NDM * NKP : 0;
+    double *dpx = drs + NDM * NFRS;                        // ROW: D_pr | D_ps of the current row
+    double *kpanel = dpx + NDM * NKP;                      // ROW: K_pr | K_ps of the current row
+    uint32_t *queue = (uint32_t *)(drs + NDM * NFRS + ROWD);
+    double *slots = drs + NDM * NFRS + ROWD + (qcap + 1) / 2;
+    double *gsets = tm + ((8 + nrs * 5 + NDM * NFRS + ROWD + (qcap + 1) / 2 + nqs * slot_d + 1) & ~1);
 
     const int nbas = t.nbas;
     const int nao = t.nao;
@@ -219,22 +230,53 @@ rys_jk_warp_kernel(JKTask t)
         // ---------------- next X pair of this team ----------------
         jkw_team_sync<TW>(team);
         if (lt == 0) {
-            tm_ints[0] = atomicAdd(t.head, 1) * t.world + t.rank;
-            tm_ints[1] = 0;
+            if (ROW) {
+                *(long long *)tm = (long long)atomicAdd((unsigned long long *)t.head, 1ull) * t.world + t.rank;
+            } else {
+                tm_ints[0] = atomicAdd(t.head, 1) * t.world + t.rank;
+            }
             tm_ints[2] = 0;
+            tm_ints[3] = 0;
         }
         jkw_team_sync<TW>(team);
-        // work item = (X pair ix, chunk of the q-sorted Y list); chunk-major order
+        // flat: work item = (X pair ix, chunk of the q-sorted Y list); chunk-major order
         // so that the dense leading chunks of every X pair are handed out first
-        const int item = tm_ints[0];
-        if (item >= t.npair_x * t.nychunk) break;
-        const int chunk = item / t.npair_x;
-        const int ix = item - chunk * t.npair_x;
+        // ROW : work item = (X pair ix, block of rows), row-block major
+        int ix, ypos = 0, y_end = 0, row_begin = 0, row_end = 1;
+        if (ROW) {
+            const long long item = *(const long long *)tm;
+            if (item >= (long long)t.npair_x * t.nrowblk) break;
+            const int rb = (int)(item / t.npair_x);
+            ix = (int)(item - (long long)rb * t.npair_x);
+            row_begin = rb * t.rows_per_item;
+            row_end = min(t.nrows, row_begin + t.rows_per_item);
+        } else {
+            const int item = tm_ints[0];
+            if (item >= t.npair_x * t.nychunk) break;
+            const int chunk = item / t.npair_x;
+            ix = item - chunk * t.npair_x;
+            ypos = chunk * t.ychunk;
+            if (t.dedupe == 1 && ypos < ix) ypos = ix;
+            y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
+        }
         const float thr = t.cutoff - t.q_x[ix];
-        int ypos = chunk * t.ychunk;
-        if (t.dedupe == 1 && ypos < ix) ypos = ix;
-        const int y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
-        if (ypos >= y_end || t.q_y[ypos] + t.dm_penalty + t.q_margin < thr) continue;   // dead chunk
+        if (ROW) {
+            bool any_row = false;
+            for (int row = row_begin + lt; row < row_end; row += TEAM)
+                any_row = any_row || (t.row_qmax[row] + t.dm_penalty >= thr);
+            if (TW == 1) {
+                if (!__any_sync(0xffffffffu, any_row)) continue;
+            } else {
+                if (any_row) tm_ints[2] = 1;
+                jkw_team_sync<TW>(team);
+                const int alive = tm_ints[2];
+                jkw_team_sync<TW>(team);
+                if (lt == 0) tm_ints[2] = 0;
+                if (!alive) continue;
+            }
+        } else {
+            if (ypos >= y_end || t.q_y[ypos] + t.dm_penalty + t.q_margin < thr) continue;   // dead chunk
+        }
         const uint32_t pair_rs = t.pair_x[ix];
         const int rsh = pair_rs / nbas;
         const int ssh = pair_rs - rsh * nbas;
@@ -287,6 +329,49 @@ rys_jk_warp_kernel(JKTask t)
         const float *dc_r = t.dm_cond + (size_t)rsh * nbas;
         const float *dc_s = t.dm_cond + (size_t)ssh * nbas;
         const float d_rs = dc_r[ssh];
+        // K_pr / K_ps partial sums of this lane: per quartet (flat) or over the whole row (ROW)
+        double accp[NDM][NC], accs[NDM][NFS];
+        int psh_row = 0;
+        float d_uni = -1e30f;
+        const float *dc_prow = t.dm_cond;
+        jkw_team_sync<TW>(team);
+
+        for (int row = row_begin; row < row_end; ++row) {
+        if (ROW) {
+            // ---------------- next row: shell p, its partners [ypos, y_end) ----------------
+            if (t.row_qmax[row] + t.dm_penalty < thr) continue;
+            psh_row = t.row_p[row];
+            const int p0 = ao_loc[psh_row];
+            ypos = t.row_ptr[row];
+            y_end = t.row_ptr[row + 1];
+            dc_prow = t.dm_cond + (size_t)psh_row * nbas;
+            d_uni = -1e30f;                               // team-uniform part of the density bound
+            if (do_j) d_uni = d_rs;
+            if (do_k) d_uni = fmaxf(d_uni, fmaxf(dc_r[psh_row], dc_s[psh_row]));
+            jkw_team_sync<TW>(team);
+            if (do_k) {
+                for (int i = lt; i < NDM * NKP; i += TEAM) {
+                    const int idm = i / NKP;
+                    const int ak = i - idm * NKP;
+                    const int ia = ak / (NFR + NFS);
+                    const int k = ak - ia * (NFR + NFS);
+                    const int col = k < NFR ? r0 + k : s0 + k - NFR;
+                    dpx[i] = __ldg(t.dm + idm * nao2 + (size_t)(p0 + ia) * nao + col);
+                    kpanel[i] = 0.;
+                }
+            }
+#pragma unroll
+            for (int idm = 0; idm < NDM; ++idm) {
+#pragma unroll
+                for (int n = 0; n < NC; ++n) accp[idm][n] = 0.;
+#pragma unroll
+                for (int d = 0; d < NFS; ++d) accs[idm][d] = 0.;
+            }
+            if (TW > 1 && lt == 0) {
+                tm_ints[2] = 0;
+                tm_ints[3] = 0;
+            }
+        }
         int qn = 0;
         int exhausted = 0;
         jkw_team_sync<TW>(team);
@@ -298,6 +383,22 @@ rys_jk_warp_kernel(JKTask t)
                 bool keep = false, stop = false;
                 if (y >= y_end) {
                     stop = true;
+                } else if (ROW) {
+                    // rows are not q-sorted: every partner of p is tested
+                    const float qy = t.q_y[y];
+                    keep = qy + t.dm_penalty >= thr;
+                    if (keep) {
+                        const int qsh = t.pair_y[y] - (uint32_t)psh_row * nbas;
+                        if (t.dedupe) {
+                            const uint32_t canon = psh_row >= qsh ? (uint32_t)psh_row * nbas + qsh
+                                                                  : (uint32_t)qsh * nbas + psh_row;
+                            keep = canon >= pair_rs;
+                        }
+                        float dmax = d_uni;
+                        if (do_j) dmax = fmaxf(dmax, dc_prow[qsh]);
+                        if (do_k) dmax = fmaxf(dmax, fmaxf(dc_r[qsh], dc_s[qsh]));
+                        keep = keep && (dmax + qy > thr);
+                    }
                 } else {
                     float qy = t.q_y[y];
                     if (qy + t.dm_penalty + t.q_margin < thr) {
@@ -326,7 +427,7 @@ rys_jk_warp_kernel(JKTask t)
                 int base = qn;
                 if (TW > 1) {
                     base = 0;
-                    if (lane == 0 && cnt) base = atomicAdd(&tm_ints[1], cnt);
+                    if (lane == 0 && cnt) base = atomicAdd(&tm_ints[2], cnt);
                     base = __shfl_sync(0xffffffffu, base, 0);
                 }
                 if (keep) queue[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)y;
@@ -335,10 +436,10 @@ rys_jk_warp_kernel(JKTask t)
                     exhausted = __any_sync(0xffffffffu, stop);
                     __syncwarp();
                 } else {
-                    if (stop) tm_ints[2] = 1;
+                    if (stop) tm_ints[3] = 1;
                     jkw_team_sync<TW>(team);
-                    qn = tm_ints[1];
-                    exhausted = tm_ints[2];
+                    qn = tm_ints[2];
+                    exhausted = tm_ints[3];
                     jkw_team_sync<TW>(team);
                 }
                 ypos += TEAM;
@@ -364,7 +465,16 @@ rys_jk_warp_kernel(JKTask t)
                         sl[3] = rec[3]; sl[4] = rec[4]; sl[5] = rec[5];
                         double fac = PI_FAC * t.scale * rec[7];
                         if (rsh == ssh) fac *= .5;
-                        if (t.dedupe == 1 && iy == ix) fac *= .5;
+                        if (ROW) {
+                            if (t.dedupe) {
+                                const int qsh = t.pair_y[iy] - (uint32_t)psh_row * nbas;
+                                const uint32_t canon = psh_row >= qsh ? (uint32_t)psh_row * nbas + qsh
+                                                                      : (uint32_t)qsh * nbas + psh_row;
+                                if (canon == pair_rs) fac *= .5;
+                            }
+                        } else if (t.dedupe == 1 && iy == ix) {
+                            fac *= .5;
+                        }
                         sl[6] = active ? fac : 0.;
                         sl[7] = rec[6];                    // (p0, q0)
                     }
@@ -669,9 +779,26 @@ rys_jk_warp_kernel(JKTask t)
                         for (int d = 0; d < NFS; ++d) kqs[d] = 0.;
                         if (on) {
                             double dqs[NFS], dps[NFS];
+                            double dqr[NC], dpr[NC];
+                            if (ROW) {
+                                // q is the column index: neighbouring partners of p -> neighbouring addresses;
+                                // the p rows come from the block staged at the row start
+                                const double *dT = t.dmT + idm * nao2 + q0 + bb;
+                                const double *dp = dpx + idm * NKP + a * (NFR + NFS);
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) {
+                                    dqs[d] = __ldg(dT + (size_t)(s0 + d) * nao);
+                                    dps[d] = dp[NFR + d];
+                                }
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) {
+                                    const int c = c0 + n < NFR ? c0 + n : NFR - 1;
+                                    dqr[n] = __ldg(dT + (size_t)(r0 + c) * nao);
+                                    dpr[n] = dp[c];
+                                }
+                            } else {
                             ld_row<NFS>(dqs, dm + qrow + s0, vec_s);
                             ld_row<NFS>(dps, dm + prow + s0, vec_s);
-                            double dqr[NC], dpr[NC];
                             if (NCS == 1) {
                                 ld_row<NC>(dqr, dm + qrow + r0, vec_r);
                                 ld_row<NC>(dpr, dm + prow + r0, vec_r);
@@ -682,6 +809,7 @@ rys_jk_warp_kernel(JKTask t)
                                     dqr[n] = __ldg(dm + qrow + r0 + c);
                                     dpr[n] = __ldg(dm + prow + r0 + c);
                                 }
+                            }
                             }
 #pragma unroll
                             for (int n = 0; n < NC; ++n) {
@@ -707,14 +835,24 @@ rys_jk_warp_kernel(JKTask t)
                             lead_q = a == 0;
                         }
                         if (on && lead_q) {
+                            if (ROW) {
+                                double *kT = t.vkT + idm * nao2 + q0 + bb;
+#pragma unroll
+                                for (int n = 0; n < NC; ++n)
+                                    if (c0 + n < NFR) JK_ATOMIC_ADD(kT + (size_t)(r0 + c0 + n) * nao, kqr[n]);
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(kT + (size_t)(s0 + d) * nao, kqs[d]);
+                            } else {
 #pragma unroll
                             for (int n = 0; n < NC; ++n)
                                 if (c0 + n < NFR) JK_ATOMIC_ADD(vk + qrow + r0 + c0 + n, kqr[n]);
 #pragma unroll
                             for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + qrow + s0 + d, kqs[d]);
+                            }
                         }
-                        // K_p* rows: complete after the b loop (BL) or after the shuffle over b
-                        if (last) {
+                        // K_p* rows: complete after the b loop (BL) or after the shuffle over b;
+                        // ROW: they keep accumulating until the row ends
+                        if (last && !ROW) {
                             bool lead_p = true;
                             if (!BL && SHFL_RED && NFQ > 1) {
 #pragma unroll
@@ -739,13 +877,14 @@ rys_jk_warp_kernel(JKTask t)
                 // K different quartets per lane slot, one primitive quartet each
                 build_gsets(0);
                 for (int k = 0; k < K; ++k) {
-                    double accp[NDM][NC], accs[NDM][NFS];
+                    if (!ROW) {
 #pragma unroll
-                    for (int idm = 0; idm < NDM; ++idm) {
+                        for (int idm = 0; idm < NDM; ++idm) {
 #pragma unroll
-                        for (int n = 0; n < NC; ++n) accp[idm][n] = 0.;
+                            for (int n = 0; n < NC; ++n) accp[idm][n] = 0.;
 #pragma unroll
-                        for (int d = 0; d < NFS; ++d) accs[idm][d] = 0.;
+                            for (int d = 0; d < NFS; ++d) accs[idm][d] = 0.;
+                        }
                     }
 #pragma unroll
                     for (int bi = 0; bi < NBL; ++bi) {
@@ -762,13 +901,14 @@ rys_jk_warp_kernel(JKTask t)
             } else {
                 // contracted class (BL == 0 only): K primitive quartets of the same quartet per pass
                 double gout[NC][NFS];
-                double accp[NDM][NC], accs[NDM][NFS];
+                if (!ROW) {
 #pragma unroll
-                for (int idm = 0; idm < NDM; ++idm) {
+                    for (int idm = 0; idm < NDM; ++idm) {
 #pragma unroll
-                    for (int n = 0; n < NC; ++n) accp[idm][n] = 0.;
+                        for (int n = 0; n < NC; ++n) accp[idm][n] = 0.;
 #pragma unroll
-                    for (int d = 0; d < NFS; ++d) accs[idm][d] = 0.;
+                        for (int d = 0; d < NFS; ++d) accs[idm][d] = 0.;
+                    }
                 }
 #pragma unroll
                 for (int n = 0; n < NC; ++n)
@@ -791,11 +931,46 @@ rys_jk_warp_kernel(JKTask t)
             if (lt < rem) queue[lt] = keepv;
             qn = rem;
             if (TW > 1) {
-                if (lt == 0) tm_ints[1] = rem;
+                if (lt == 0) tm_ints[2] = rem;
             }
             jkw_team_sync<TW>(team);
             if (exhausted && qn == 0) break;
         }
+
+        if (ROW && do_k) {
+            // ---------------- row end: K_pr / K_ps leave the team ----------------
+            // lanes holding the same p component a add to the same panel entries: one round per
+            // (quartet slot, b, c part), so that every round touches each entry at most once
+            constexpr int NROUND = NSW * NBLANE * NCS;
+            const int myround = (s4 * NBLANE + (BL ? 0 : b)) * NCS + cpart;
+            for (int rd = 0; rd < NROUND; ++rd) {
+                if (lane_on && myround == rd) {
+                    double *kp = kpanel + a * (NFR + NFS);
+#pragma unroll
+                    for (int idm = 0; idm < NDM; ++idm) {
+#pragma unroll
+                        for (int n = 0; n < NC; ++n)
+                            if (c0 + n < NFR) kp[idm * NKP + c0 + n] += accp[idm][n];
+#pragma unroll
+                        for (int d = 0; d < NFS; ++d) kp[idm * NKP + NFR + d] += accs[idm][d];
+                    }
+                }
+                jkw_team_sync<TW>(team);
+            }
+            const int p0 = ao_loc[psh_row];
+            for (int i = lt; i < NDM * NKP; i += TEAM) {
+                const double v = kpanel[i];
+                if (v != 0.) {
+                    const int idm = i / NKP;
+                    const int ak = i - idm * NKP;
+                    const int ia = ak / (NFR + NFS);
+                    const int k = ak - ia * (NFR + NFS);
+                    const int col = k < NFR ? r0 + k : s0 + k - NFR;
+                    JK_ATOMIC_ADD(t.vk + idm * nao2 + (size_t)(p0 + ia) * nao + col, v);
+                }
+            }
+        }
+        }   // rows of the work item (one pass when !ROW)
 
         // ---------------- flush J_rs ----------------
         if (do_j) {

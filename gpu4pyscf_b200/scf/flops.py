@@ -26,7 +26,11 @@ def f_dig(li, lj, lk, ll, n_dm=1, with_j=True, with_k=True):
 
 def f_quartet(lprim, n_dm=1, with_j=True, with_k=True):
     '''lprim = (li, lj, lk, ll, npi, npj, npk, npl) -> flops of one shell quartet'''
-    li, lj, lk, ll, a, b, c, d = lprim
-    # the 2D recurrences are evaluated with the higher-l pair as given by the
-    # class; F_2d is not symmetric, take the canonical (li >= lj, lk >= ll) form
-    return a * b * c * d * f_prim(li, lj, lk, ll) + f_dig(li, lj, lk, ll, n_dm, with_j, with_k)
+    li, lj, lk, ll, a, b, c, d = lprim[:8]
+    # F_2d is not symmetric in bra and ket, and a launch may stream either pair: count every class
+    # in its canonical form (SURVEY.md appendix D: li >= lj, lk >= ll, (li, lj) >= (lk, ll)) so that
+    # F_alg does not depend on which pair a kernel happens to stream
+    bra, ket = (max(li, lj), min(li, lj)), (max(lk, ll), min(lk, ll))
+    if ket > bra:
+        bra, ket = ket, bra
+    return a * b * c * d * f_prim(*bra, *ket) + f_dig(li, lj, lk, ll, n_dm, with_j, with_k)

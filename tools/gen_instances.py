@@ -151,15 +151,42 @@ def rowt_ok(lp, lq, lr, ls, ndm):
 
 
 def row_classes():
-    """(lp, lq, lr, ls, kind) with lp >= lq (q = streamed shell), lr >= ls; every orientation
-    that fits is instantiated, the host picks per launch."""
+    """(lp, lq, lr, ls, kind) with lp >= lq (q = streamed shell), lr >= ls.  kind 't': thread per
+    quartet (every orientation that fits is instantiated, the host picks per launch); kind 'w':
+    warp-team kernel, instantiated with the lowest angular momentum of the class as the streamed
+    shell (for equal lq, ls: the orientation the lane/tile model prefers)."""
     types = [(a, b) for a in range(LMAX + 1) for b in range(a + 1)]
     out = []
     for y in types:
         for x in types:
             if rowt_ok(y[0], y[1], x[0], x[1], 1):
                 out.append((y[0], y[1], x[0], x[1], 't'))
+                continue
+            if not WARP_KERNEL or y[1] > x[1]:
+                continue
+            a = warp_cfg(y, x, 1)
+            if a is None:
+                continue
+            if y[1] == x[1] and y != x and not rowt_ok(x[0], x[1], y[0], y[1], 1):
+                b = warp_cfg(x, y, 1)
+                if b is not None and (b[0] > a[0] + 1e-9 or (abs(b[0] - a[0]) <= 1e-9 and x > y)):
+                    continue            # the other orientation is the instantiated one
+            out.append((y[0], y[1], x[0], x[1], 'w'))
     return out
+
+
+def warp_variants(lp, lq, lr, ls, ndm):
+    """(ncs of the general kernel, ncs of the b-loop variant or None)"""
+    wc = warp_cfg((lp, lq), (lr, ls), ndm)
+    if wc is None:
+        return None
+    bl = None
+    if BL_ENABLE and CHOOSER == 'cost' and lq > 0:
+        bl = warp_cfg_cost((lp, lq), (lr, ls), ndm, bl=True)
+        # measured on Taxol: pays off for unsplit register tiles only
+        if bl is not None and (-bl[0] > BL_GAIN * -wc[0] or bl[1] != 1):
+            bl = None
+    return wc[1], (bl[1] if bl is not None else None)
 
 
 def main(dst):
@@ -218,12 +245,26 @@ def main(dst):
     for n, (lp, lq, lr, ls, kind) in enumerate(rcls):
         with open(os.path.join(dst, 'jk_inst_%02d.cu' % (n % NUNITS)), 'a') as f:
             for ndm in (1, 2):
-                if kind == 't' and not rowt_ok(lp, lq, lr, ls, ndm):
-                    continue
                 name = 'jk_launch_row_%d%d%d%d_%d' % (lp, lq, lr, ls, ndm)
-                f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
-                        '{ return jk_launch_rowt<%d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
-                        % (name, lp, lq, lr, ls, ndm))
+                if kind == 't' and rowt_ok(lp, lq, lr, ls, ndm):
+                    f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
+                            '{ return jk_launch_rowt<%d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
+                            % (name, lp, lq, lr, ls, ndm))
+                    rdecls.append((lp, lq, lr, ls, ndm, name))
+                    continue
+                wv = warp_variants(lp, lq, lr, ls, ndm) if WARP_KERNEL else None
+                if wv is None:
+                    continue
+                if wv[1] is not None:
+                    f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
+                            '{\n    if (t->nprim_p * t->nprim_q * t->nprim_r * t->nprim_s == 1)\n'
+                            '        return jk_launch_warp<%d, %d, %d, %d, %d, %d, 1, 1>(t, nsm, smem_max, s);\n'
+                            '    return jk_launch_warp<%d, %d, %d, %d, %d, %d, 0, 1>(t, nsm, smem_max, s);\n}\n'
+                            % (name, lp, lq, lr, ls, wv[1], ndm, lp, lq, lr, ls, wv[0], ndm))
+                else:
+                    f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
+                            '{ return jk_launch_warp<%d, %d, %d, %d, %d, %d, 0, 1>(t, nsm, smem_max, s); }\n'
+                            % (name, lp, lq, lr, ls, wv[0], ndm))
                 rdecls.append((lp, lq, lr, ls, ndm, name))
     with open(os.path.join(dst, 'jk_dispatch.inc'), 'w') as f:
         f.write('// GENERATED by tools/gen_instances.py\n')
