@@ -258,6 +258,14 @@ static int build_rows_impl(double *vj, double *vk, double *vkT, const double *dm
 
 extern "C" {
 
+// kernel family that serves a class: 0 none, 1 thread per quartet, 2 warp team, 3 block slots
+int B200_class_kind(int lp, int lq, int lr, int ls, int row)
+{
+    if (lp < 0 || lq < 0 || lr < 0 || ls < 0) return 0;
+    if (lp > LMAX_B200 || lq > LMAX_B200 || lr > LMAX_B200 || ls > LMAX_B200) return 0;
+    return jk_class_kind(lp, lq, lr, ls, row ? 1 : 0);
+}
+
 int B200_has_row_class(int lp, int lq, int lr, int ls)
 {
     if (lp < 0 || lq < 0 || lr < 0 || ls < 0) return 0;
@@ -332,13 +340,25 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
                  uint32_t *pool, int *bas, double *env)
 {
     (void)shm_size; (void)s_cond_ij; (void)s_cond_kl; (void)diffuse_exps;
+    // env[8] = omega, libcint convention (reference: rys_roots_rs, rys_roots.cu:91-119): 0 full range,
+    // > 0 long range erf(omega r)/r, < 0 short range erfc(|omega| r)/r = full - long
+    const double omega = env[8];
+    if (omega >= 0.)
+        return build_group(vj, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
+                           pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
+                           dm_cond, cutoff, dm_penalty, pool, bas, omega, 1.);
+    int err = build_group(vj, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
+                          pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
+                          dm_cond, cutoff, dm_penalty, pool, bas, 0., 1.);
+    if (err) return err;
     return build_group(vj, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
                        pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
-                       dm_cond, cutoff, dm_penalty, pool, bas, env[8], 1.);
+                       dm_cond, cutoff, dm_penalty, pool, bas, -omega, -1.);
 }
 
-// K only, with range separation: lr_factor * K[erf(|omega| r)/r] + sr_factor * K[erfc(|omega| r)/r]
-// = sr_factor * K[1/r] + (lr_factor - sr_factor) * K[erf(|omega| r)/r]; omega == 0: plain K.
+// K only, operator lr_factor * erf(|omega| r)/r + sr_factor * erfc(|omega| r)/r with the reference's
+// conventions (rys_roots_for_k.cu:25-60): omega == 0 -> lr_factor * K[1/r]; sr_factor == 0 ->
+// lr_factor * K[erf]; otherwise sr_factor * K[1/r] + (lr_factor - sr_factor) * K[erf].
 int RYS_build_k(double *vk, double *dm, int n_dm, int nao, double omega, double lr_factor, double sr_factor,
                 RysIntEnvVars *envs, int *shls_slice, int shm_size, int npairs_ij, int npairs_kl,
                 uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
@@ -347,8 +367,14 @@ int RYS_build_k(double *vk, double *dm, int n_dm, int nao, double omega, double 
                 uint32_t *pool, int *bas)
 {
     (void)shm_size; (void)s_cond_ij; (void)s_cond_kl; (void)diffuse_exps;
-    double c_full = 1., c_lr = 0.;
-    if (omega != 0.) {
+    double c_full, c_lr;
+    if (omega == 0.) {
+        c_full = lr_factor;
+        c_lr = 0.;
+    } else if (sr_factor == 0.) {
+        c_full = 0.;
+        c_lr = lr_factor;
+    } else {
         c_full = sr_factor;
         c_lr = lr_factor - sr_factor;
     }

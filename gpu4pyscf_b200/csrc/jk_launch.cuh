@@ -122,19 +122,20 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     }
     int nteams = jkw_block_threads(C::TEAM, C::TILE * (1 + NDM)) / C::TEAM;
     const int nprimq = npq * nrs;
-    if (BL && nprimq != 1) {
-        fprintf(stderr, "rys_jk_warp: the b-loop variant only handles uncontracted launches\n");
+    if ((BL || ROW) && nprimq != 1) {
+        fprintf(stderr, "rys_jk_warp: the b-loop and row-stream variants only handle uncontracted launches\n");
         return 1;
     }
-    // g-sets per lane slot: fill (not overfill) the team in the recurrence phase,
-    // whose work items are (g-set, root, axis)
+    // g-sets per lane slot: fill (not overfill) the team in the root/recurrence phase,
+    // whose work items are (g-set, root)
 #ifndef JKW_K_BIAS
 #define JKW_K_BIAS 0
 #endif
-    int K = C::TEAM / (C::NSW * 3 * C::NROOTS) + JKW_K_BIAS;
+    int K = C::TEAM / (C::NSW * C::NROOTS) + JKW_K_BIAS;      // lanes of the root/recurrence phase: (g-set, root)
     if (K > 4) K = 4;
     if (K < 1) K = 1;
     if (nprimq > 1 && K > nprimq) K = nprimq;
+    if (ROW) K = C::KROW;                                     // compile-time shape of the row-stream kernels
     const int minb = jkw_minblocks(C::TILE, NDM, NCS == 1 ? C::SUBSIZE : LS + 1, C::TEAM);
     const int rowd = ROW ? 2 * NDM * C::NFP * (C::NFR + C::NFS) : 0;
     auto smem_of = [&](int k) {
@@ -142,7 +143,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
                 + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET, rowd)) * 8;
     };
     const int budget = (smem_max + 1024) / minb - 1024;
-    while (K > 1 && smem_of(K) > budget) --K;
+    while (!ROW && K > 1 && smem_of(K) > budget) --K;
     while (nteams > 1 && smem_of(K) > smem_max) --nteams;     // fewer teams per block for the fattest classes
     const int nt = nteams * C::TEAM;
     int smem = smem_of(K);

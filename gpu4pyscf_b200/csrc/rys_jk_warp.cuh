@@ -54,9 +54,77 @@ struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
     static constexpr int SEG = NCS == 1 ? B::LRS + 1 : B::SUBSIZE;
     static constexpr int SUBP = oddhalf(SEG);
     static constexpr int GSIZEP = oddhalf((LP + 1) * (LQ + 1) * SUBP);
-    static constexpr int GSET = oddhalf(2 * B::NROOTS + 3 * B::NROOTS * GSIZEP);
+    static constexpr int GSET0 = oddhalf(2 * B::NROOTS + 3 * B::NROOTS * GSIZEP);
+    // Bank conflicts of the 16-byte accesses to the g-sets for a g-set stride of `gset` doubles:
+    // (a) contraction loads -- lane (quartet slot, a, b) reads the segment of its (ea, eb) on every
+    // axis; (b) stores of the merged root/recurrence phase -- lane (g-set, root).  A quarter warp
+    // (8 lanes) is served in one wavefront when its distinct addresses fall in distinct 16-byte
+    // bank groups; returns the excess wavefronts.
+    static constexpr int gset_conflicts(int gset)
+    {
+        int excess = 0;
+        for (int mode = 0; mode < 4; ++mode) {                 // 0..2: loads on axis x, y, z; 3: stores
+            for (int qw = 0; qw < 4; ++qw) {
+                int addr[8] = {0}, n = 0;
+                for (int l = qw * 8; l < qw * 8 + 8; ++l) {
+                    int off = -1;
+                    if (mode < 3) {
+                        const int s4 = TW == 1 ? l / G : 0;
+                        if (TW == 1 && s4 >= NSW) continue;
+                        const int tg = TW == 1 ? l - s4 * G : l;
+                        if (tg >= G) continue;
+                        const int ab = tg / NCS;
+                        const int a = BL ? ab : ab / B::NFQ;
+                        const int b = BL ? 0 : ab - a * B::NFQ;
+                        const int ea = mode == 0 ? cart_x(LP, a) : (mode == 1 ? cart_y(LP, a) : cart_z(LP, a));
+                        const int eb = mode == 0 ? cart_x(LQ, b) : (mode == 1 ? cart_y(LQ, b) : cart_z(LQ, b));
+                        off = s4 * gset + 2 * B::NROOTS + mode * GSIZEP + (ea * (LQ + 1) + eb) * SUBP;
+                    } else {
+                        const int g = l / B::NROOTS, root = l - g * B::NROOTS;
+                        if (g >= NSW * 4) continue;
+                        off = g * gset + 2 * B::NROOTS + root * 3 * GSIZEP;
+                    }
+                    bool dup = false;
+                    for (int i = 0; i < n; ++i) dup = dup || addr[i] == off / 2;
+                    if (!dup) addr[n++] = off / 2;
+                }
+                int cnt[8] = {0}, worst = 0;
+                for (int i = 0; i < n; ++i) {
+                    const int grp = addr[i] & 7;
+                    cnt[grp]++;
+                    worst = cnt[grp] > worst ? cnt[grp] : worst;
+                }
+                excess += worst > 1 ? worst - 1 : 0;
+            }
+        }
+        return excess;
+    }
+    // smallest padding (< 16 doubles) of the g-set stride with the fewest conflicts
+    static constexpr int best_gset()
+    {
+        int best = GSET0, cost = gset_conflicts(GSET0);
+        for (int pad = 2; pad < 16; pad += 2) {
+            const int c = gset_conflicts(GSET0 + pad);
+            if (c < cost) {
+                cost = c;
+                best = GSET0 + pad;
+            }
+        }
+        return best;
+    }
+    static constexpr int GSET = best_gset();
     // registers: gout + J_rs accumulators + one root's gx/gy/gz tile
     static constexpr int TILE = B::NC * B::NFS;
+    // row-stream (uncontracted) kernels: quartets per lane slot such that the (g-set, root) lanes of
+    // the merged root/recurrence phase fill the team, within 16 KB of g-sets per team
+    static constexpr int krow()
+    {
+        int k = TEAM / (NSW * B::NROOTS);
+        k = k > 4 ? 4 : (k < 1 ? 1 : k);
+        while (k > 1 && NSW * k * GSET * 8 > 16384) --k;
+        return k;
+    }
+    static constexpr int KROW = krow();
 };
 
 #define JKW_SLOT_HDR 8       // AB[3], A[3], fac, (p0,q0)
@@ -172,11 +240,13 @@ rys_jk_warp_kernel(JKTask t)
     rys_stage_tables<NROOTS>(rys_tab, t.rys_cheb, t.rys_large, tid, blockDim.x);
     __syncthreads();
 
-    const int npq = t.nprim_p * t.nprim_q;
-    const int nrs = t.nprim_r * t.nprim_s;
+    // ROW kernels serve uncontracted launches only: every shape below is a compile-time constant
+    constexpr bool SNG = ROW != 0;
+    const int npq = SNG ? 1 : t.nprim_p * t.nprim_q;
+    const int nrs = SNG ? 1 : t.nprim_r * t.nprim_s;
     const int nprimq = npq * nrs;
-    const bool single = nprimq == 1;
-    const int K = t.nq;                      // g-sets per lane slot
+    const bool single = SNG || nprimq == 1;
+    const int K = SNG ? C::KROW : t.nq;      // g-sets per lane slot
     const int ngs = NSW * K;
     const int nqs = single ? ngs : NSW;      // quartets per batch
     const int qcap = nqs + TEAM;
@@ -514,12 +584,80 @@ rys_jk_warp_kernel(JKTask t)
                     pi[1] = ao_loc[qsh];
                 }
             }
-            // phases 1-2 of one pass: roots/weights and 2D integrals of every g-set of the team
+            // 2D integrals of one (g-set, root, axis): VRR + TRR in registers, bra HRR (and the ket
+            // HRR when the tile is split), result to shared memory as
+            // g[root*3+axis][(ea, eb)][segment], (ea, eb) segments SUBP apart
+            auto recur_axis = [&](double *gs, const double *sl, const double P, const double Q, const int ra,
+                                  const int axis, const double g00, const double rt_aij, const double rt_akl,
+                                  const double b00, const double b10, const double b01) {
+                const double PQ = P - Q;
+                const double c0p = (P - sl[3 + axis]) - rt_aij * PQ;
+                const double cpq = (Q - rsgeom[3 + axis]) + rt_akl * PQ;
+                double gg[LRS + 1][LPQ + 1];
+                gg[0][0] = g00;
+                if (LPQ > 0) {
+                    gg[0][1] = c0p * gg[0][0];
+#pragma unroll
+                    for (int e = 1; e < LPQ; ++e)
+                        gg[0][e + 1] = c0p * gg[0][e] + e * b10 * gg[0][e - 1];
+                }
+                if (LRS > 0) {
+                    gg[1][0] = cpq * gg[0][0];
+#pragma unroll
+                    for (int e = 1; e <= LPQ; ++e)
+                        gg[1][e] = cpq * gg[0][e] + e * b00 * gg[0][e - 1];
+#pragma unroll
+                    for (int f = 1; f < LRS; ++f) {
+                        gg[f + 1][0] = cpq * gg[f][0] + f * b01 * gg[f - 1][0];
+#pragma unroll
+                        for (int e = 1; e <= LPQ; ++e)
+                            gg[f + 1][e] = cpq * gg[f][e] + f * b01 * gg[f - 1][e] + e * b00 * gg[f][e - 1];
+                    }
+                }
+                const double AB = sl[axis];
+                const double CD = rsgeom[axis];
+                double *o = gs + 2 * NROOTS + ra * GSIZEP;
+#pragma unroll
+                for (int eb = 0; eb <= LQ; ++eb) {
+                    // gg[f][ea] now holds the bra-transferred value for (ea, eb)
+#pragma unroll
+                    for (int ea = 0; ea <= LP; ++ea) {
+                        double v[LRS + 1];
+#pragma unroll
+                        for (int f = 0; f <= LRS; ++f) v[f] = gg[f][ea];
+                        if (NCS == 1) {
+                            jkw_st_seg<LRS + 1>(o + (ea * (LQ + 1) + eb) * SUBP, v);
+                        } else {
+                            double seg[SUB];
+#pragma unroll
+                            for (int d = 0; d <= LS; ++d) {
+#pragma unroll
+                                for (int c = 0; c <= LR; ++c) seg[c * (LS + 1) + d] = v[c];
+                                if (d < LS) {
+#pragma unroll
+                                    for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
+                                }
+                            }
+                            jkw_st_seg<SUB>(o + (ea * (LQ + 1) + eb) * SUBP, seg);
+                        }
+                    }
+                    if (eb < LQ) {
+#pragma unroll
+                        for (int f = 0; f <= LRS; ++f)
+#pragma unroll
+                            for (int e = 0; e < LPQ - eb; ++e) gg[f][e] = gg[f][e + 1] + AB * gg[f][e];
+                    }
+                }
+            };
+            // roots, weights and 2D integrals of every g-set of the team, ONE phase: a lane owns a
+            // (g-set, root) -- the scalars of the primitive quartet (one rsqrt, one division), both
+            // Rys series, then the three axes.  Uncontracted launches: g-set = quartet slot;
+            // contracted: g-set k*NSW+j = primitive quartet pass*K+k of quartet slot j.
             auto build_gsets = [&](const int pass) {
-                // ---------------- phase 1: roots and weights of every g-set ----------------
-                for (int it = lt; it < ngs * 2 * NROOTS; it += TEAM) {
-                    const int g = it / (2 * NROOTS);
-                    const int idx = it - g * (2 * NROOTS);
+                if (pass > 0) jkw_team_sync<TW>(team);      // the previous pass has been contracted by every lane
+                for (int it = lt; it < ngs * NROOTS; it += TEAM) {
+                    const int g = it / NROOTS;
+                    const int root = it - g * NROOTS;
                     int j = g, pi = 0;
                     if (!single) {
                         const int k = g / NSW;
@@ -533,113 +671,33 @@ rys_jk_warp_kernel(JKTask t)
                     const double *sl = slots + j * slot_d;
                     const double *pp = sl + JKW_SLOT_HDR + ipq * 5;
                     const double *rr = rsprim + irs * 5;
-                    double zeta = pp[0], eta = rr[0];
-                    double dx = pp[1] - rr[1], dy = pp[2] - rr[2], dz = pp[3] - rr[3];
-                    double ze = zeta + eta;
-                    double theta = zeta * eta / ze;
+                    const double zeta = pp[0], eta = rr[0];
+                    const double dx = pp[1] - rr[1], dy = pp[2] - rr[2], dz = pp[3] - rr[3];
+                    const double rsq = rsqrt(zeta + eta);
+                    const double rze = rsq * rsq;                   // 1 / (zeta + eta)
+                    const double ize = 1. / (zeta * eta);
+                    const double theta = zeta * eta * rze;
                     double x = theta * (dx * dx + dy * dy + dz * dz);
-                    double lrf = 1.;                           // long-range attenuation: theta -> theta * lrf
-                    if (t.omega != 0.) {
-                        lrf = t.omega * t.omega / (t.omega * t.omega + theta);
+                    double rscale = rze;
+                    double w = valid ? sl[6] * pp[4] * rr[4] * ize * rsq : 0.;
+                    if (t.omega != 0.) {                            // long range: theta -> theta * lrf
+                        const double lrf = t.omega * t.omega / (t.omega * t.omega + theta);
                         x *= lrf;
+                        rscale *= lrf;
+                        w *= sqrt(lrf);
                     }
-                    double v = rys_value_s<NROOTS>(idx, x, rys_tab);
-                    double *rw = gsets + g * GSET;
-                    if (idx < NROOTS) {
-                        rw[idx] = v * lrf / ze;
-                    } else {
-                        double w = valid ? sl[6] * pp[4] * rr[4] / (zeta * eta * sqrt(ze)) : 0.;
-                        rw[idx] = v * w * sqrt(lrf);
-                    }
-                }
-                jkw_team_sync<TW>(team);
-                // ---------------- phase 2: VRR + TRR + HRR, one (g-set, root, axis) per lane ----------------
-                for (int it = lt; it < ngs * 3 * NROOTS; it += TEAM) {
-                    const int g = it / (3 * NROOTS);
-                    const int ra = it - g * (3 * NROOTS);
-                    const int root = ra / 3;
-                    const int axis = ra - root * 3;
-                    int j = g, pi = 0;
-                    if (!single) {
-                        const int k = g / NSW;
-                        j = g - k * NSW;
-                        pi = pass * K + k;
-                        if (pi >= nprimq) pi = 0;
-                    }
-                    const int ipq = pi / nrs;
-                    const int irs = pi - ipq * nrs;
-                    const double *sl = slots + j * slot_d;
-                    const double *pp = sl + JKW_SLOT_HDR + ipq * 5;
-                    const double *rr = rsprim + irs * 5;
+                    const double rt_aa = rys_value_s<NROOTS>(root, x, rys_tab) * rscale;
+                    const double wt = rys_value_s<NROOTS>(NROOTS + root, x, rys_tab) * w;
+                    const double rt_aij = rt_aa * eta;
+                    const double rt_akl = rt_aa * zeta;
+                    const double b00 = .5 * rt_aa;
+                    const double b10 = .5 * eta * ize * (1. - rt_aij);
+                    const double b01 = .5 * zeta * ize * (1. - rt_akl);
                     double *gs = gsets + g * GSET;
-                    double zeta = pp[0], eta = rr[0];
-                    double rt_aa = gs[root];
-                    double rt_aij = rt_aa * eta;
-                    double rt_akl = rt_aa * zeta;
-                    double b00 = .5 * rt_aa;
-                    double b10 = .5 / zeta * (1. - rt_aij);
-                    double b01 = .5 / eta * (1. - rt_akl);
-                    double P = pp[1 + axis], Q = rr[1 + axis];
-                    double PQ = P - Q;
-                    double c0p = (P - sl[3 + axis]) - rt_aij * PQ;
-                    double cpq = (Q - rsgeom[3 + axis]) + rt_akl * PQ;
-                    double gg[LRS + 1][LPQ + 1];
-                    gg[0][0] = (axis == 2) ? gs[NROOTS + root] : 1.;
-                    if (LPQ > 0) {
-                        gg[0][1] = c0p * gg[0][0];
 #pragma unroll
-                        for (int e = 1; e < LPQ; ++e)
-                            gg[0][e + 1] = c0p * gg[0][e] + e * b10 * gg[0][e - 1];
-                    }
-                    if (LRS > 0) {
-                        gg[1][0] = cpq * gg[0][0];
-#pragma unroll
-                        for (int e = 1; e <= LPQ; ++e)
-                            gg[1][e] = cpq * gg[0][e] + e * b00 * gg[0][e - 1];
-#pragma unroll
-                        for (int f = 1; f < LRS; ++f) {
-                            gg[f + 1][0] = cpq * gg[f][0] + f * b01 * gg[f - 1][0];
-#pragma unroll
-                            for (int e = 1; e <= LPQ; ++e)
-                                gg[f + 1][e] = cpq * gg[f][e] + f * b01 * gg[f - 1][e] + e * b00 * gg[f][e - 1];
-                        }
-                    }
-                    // HRR on the registers (bra, then ket), result to shared memory:
-                    // g[ra][(ea, eb)][c * (LS+1) + d], (ea, eb) segments SUBP apart
-                    const double AB = sl[axis];
-                    const double CD = rsgeom[axis];
-                    double *o = gs + 2 * NROOTS + ra * GSIZEP;
-#pragma unroll
-                    for (int eb = 0; eb <= LQ; ++eb) {
-                        // gg[f][ea] now holds the bra-transferred value for (ea, eb)
-#pragma unroll
-                        for (int ea = 0; ea <= LP; ++ea) {
-                            double v[LRS + 1];
-#pragma unroll
-                            for (int f = 0; f <= LRS; ++f) v[f] = gg[f][ea];
-                            if (NCS == 1) {
-                                jkw_st_seg<LRS + 1>(o + (ea * (LQ + 1) + eb) * SUBP, v);
-                            } else {
-                                double seg[SUB];
-#pragma unroll
-                                for (int d = 0; d <= LS; ++d) {
-#pragma unroll
-                                    for (int c = 0; c <= LR; ++c) seg[c * (LS + 1) + d] = v[c];
-                                    if (d < LS) {
-#pragma unroll
-                                        for (int c = 0; c < LRS - d; ++c) v[c] = v[c + 1] + CD * v[c];
-                                    }
-                                }
-                                jkw_st_seg<SUB>(o + (ea * (LQ + 1) + eb) * SUBP, seg);
-                            }
-                        }
-                        if (eb < LQ) {
-#pragma unroll
-                            for (int f = 0; f <= LRS; ++f)
-#pragma unroll
-                                for (int e = 0; e < LPQ - eb; ++e) gg[f][e] = gg[f][e + 1] + AB * gg[f][e];
-                        }
-                    }
+                    for (int axis = 0; axis < 3; ++axis)
+                        recur_axis(gs, sl, pp[1 + axis], rr[1 + axis], root * 3 + axis, axis,
+                                   axis == 2 ? wt : 1., rt_aij, rt_akl, b00, b10, b01);
                 }
                 jkw_team_sync<TW>(team);
             };

@@ -57,6 +57,8 @@ def load_library(name='libgvhf_rys_b200'):
         vp, vp, c_int,
         vp, vp, vp, vp, vp, vp, c_int,
         vp, c_float, c_float, c_int, c_int, c_int, vp, vp, ctypes.c_double]
+    lib.B200_class_kind.restype = c_int
+    lib.B200_class_kind.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.B200_has_row_class.restype = c_int
     lib.B200_has_row_class.argtypes = [c_int, c_int, c_int, c_int]
     lib.B200_pair_rec_stride.restype = c_int

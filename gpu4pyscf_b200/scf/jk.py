@@ -171,7 +171,7 @@ class _VHFOpt:
         # width (log units) of the q bins of the flat pair lists; 0 = exactly q-sorted lists
         self.q_bin = float(os.environ.get('B200_Q_BIN', '0.5'))
         # row-stream kernels are used when the streamed list has rows at least this long on average
-        self.row_min = float(os.environ.get('B200_ROW_MIN', '12'))
+        self.row_min = float(os.environ.get('B200_ROW_MIN', '24'))
         self._streams = None
         self._tasks = None
         self._qmax_cache = None
@@ -304,15 +304,32 @@ class _VHFOpt:
 
         def row_score(ky, kx):
             '''cost estimate of streaming ky through its row view against resident kx (lower is
-            better), or None when no row-stream kernel exists / rows are too short'''
+            better), or None when no row-stream kernel serves the launch / rows are too short'''
             if not use_rows or len(self.bas_pair_cache[ky][0]) == 0:
                 return None
             rl = self.row_list(ky)
             if rl['mean_len'] < self.row_min:
                 return None
             lr, ls_ = ls(kx)
-            if not lib.B200_has_row_class(rl['lp'], rl['lq'], lr, ls_):
+            kind = lib.B200_class_kind(rl['lp'], rl['lq'], lr, ls_, 1)
+            if kind == 0:
                 return None
+            force = os.environ.get('B200_ROW_FORCE', '0') == '1'      # measurement: skip the exclusions below
+            contracted = rl['nprim_p'] * rl['nprim_q'] != 1
+            if kind == 1 and contracted and rl['mean_len'] < 2 * self.row_min and not force:
+                return None                 # few, fat quartets per row: partially filled batches cost too much
+            if kind == 2:
+                # the row-stream warp-team kernel is specialised for uncontracted quartets
+                if contracted or int(uniq[kx[0], 1]) * int(uniq[kx[1], 1]) != 1:
+                    return None
+                # measured on Taxol: it loses against the flat kernels when the streamed shell is a
+                # d shell or higher (long unrolled b loops), and against the thread-per-quartet flat
+                # kernel for the small classes that one serves
+                if not force and rl['lq'] >= 2:
+                    return None
+                if not force and 1 in (lib.B200_class_kind(*ls(ky), lr, ls_, 0),
+                                       lib.B200_class_kind(lr, ls_, *ls(ky), 0)):
+                    return None
             scattered = _nf(rl['lq']) * (_nf(rl['lp']) + _nf(lr) + _nf(ls_))
             return scattered * (1. + 16. / rl['mean_len'])
 

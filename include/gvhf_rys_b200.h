@@ -52,9 +52,11 @@ int cuda_version(void);
  * pair_ij >= pair_kl (pair id = ish*nbas+jsh); vj/vk receive the partial
  * (un-symmetrised) sums of jk.py:594-616.  pool must hold at least one int;
  * bas and env are HOST copies (only bas is read, for l and nprim).
- * env[8] = omega (HOST): 0 or > 0 (long range); omega < 0 returns an error (the
- * caller composes short range as full - long range).  s_cond_*, diffuse_exps
- * and shm_size are accepted for signature compatibility and ignored. */
+ * env[8] = omega (HOST, libcint convention as in the reference's rys_roots_rs,
+ * lib/gvhf-rys/rys_roots.cu:91-119): 0 full range, > 0 long range erf(omega r)/r,
+ * < 0 short range erfc(|omega| r)/r (evaluated as full - long: two launches).
+ * s_cond_*, diffuse_exps and shm_size are accepted for signature compatibility
+ * and ignored (the full-range q_cond is a valid, looser Schwarz bound). */
 int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
                  RysIntEnvVars *envs, int *shls_slice, int shm_size,
                  int npairs_ij, int npairs_kl,
@@ -65,9 +67,11 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
                  uint32_t *pool, int *bas, double *env);
 
 /* Reference signature: RYS_build_k, lib/gvhf-rys/rys_contract_k.cu:605-709, called from
- * gpu4pyscf/scf/jk.py:845-877.  K only; omega == 0: plain exchange (the factors are
- * ignored); omega != 0: lr_factor * K[erf(|omega| r)/r] + sr_factor * K[erfc(|omega| r)/r],
- * evaluated as sr_factor * K[1/r] + (lr_factor - sr_factor) * K[erf] (one or two launches).
+ * gpu4pyscf/scf/jk.py:845-877.  K only, operator
+ * lr_factor * erf(|omega| r)/r + sr_factor * erfc(|omega| r)/r with the reference's rules
+ * (rys_roots_for_k.cu:25-60): omega == 0 -> lr_factor * K[1/r] (so (0,0,0) adds nothing);
+ * sr_factor == 0 -> lr_factor * K[erf]; otherwise sr_factor * K[1/r] +
+ * (lr_factor - sr_factor) * K[erf] (one or two launches).
  * Same group / pair-list / de-duplication semantics as RYS_build_jk; s_cond_*,
  * diffuse_exps and shm_size are accepted and ignored (the full-range q_cond is a valid
  * Schwarz bound for the attenuated operators). */
@@ -100,6 +104,35 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
                         double omega);
+
+/* Native entry, row-stream kernels (csrc/rys_jk_rowt.cuh, ROW variant of rys_jk_warp.cuh): one
+ * angular class with the streamed list grouped in ROWS of one shell p.
+ *   lprim  HOST int[8] = {lp, lq, lr, ls, nprim_p, nprim_q, nprim_r, nprim_s}; (p,q) is the
+ *          kernel order of the streamed pair: p the row shell, q its partners (lp >= lq)
+ *   X = (r,s) flat pair list sorted by q descending (ids r*nbas+s, r >= s)
+ *   Y: pair_y[k] = p*nbas+q, q_y[k], records rec_y (B200_pair_records on pair_y, required),
+ *      row_ptr[nrows+1] offsets, row_p[nrows] the shell of each row, row_qmax[nrows] its largest q_y
+ *   dmT / vkT: transposed density matrices and the buffer that receives the q-row K blocks
+ *      transposed (vkT[k][x][q] += K_k[q][x]); both alias dm / vk for symmetric D
+ *   dedupe != 0: the two lists come from the same group pair, a quartet is kept when
+ *      canonical(pair_y) >= pair_x (1/2 on equality)
+ *   head: zeroed device uint64 work counter; omega as in B200_build_jk_class.
+ * The warp-team kernels of this entry serve uncontracted launches only (B200_class_kind). */
+int B200_build_jk_rows(double *vj, double *vk, double *vkT, const double *dm, const double *dmT,
+                       int n_dm, int nao, const RysIntEnvVars *envs, const int *lprim,
+                       const uint32_t *pair_x, const float *q_x, int npair_x,
+                       const uint32_t *pair_y, const float *q_y, const double *rec_y,
+                       const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
+                       const float *dm_cond, float cutoff, float dm_penalty,
+                       int dedupe, int rank, int world, unsigned long long *head, void *stream, double omega);
+
+/* 1 if a row-stream kernel is instantiated for rows of (lp,lq) pairs against resident (lr,ls) pairs. */
+int B200_has_row_class(int lp, int lq, int lr, int ls);
+
+/* Kernel family that serves a class (row = 0: B200_build_jk_class, row = 1: B200_build_jk_rows):
+ * 0 none, 1 thread per quartet, 2 warp team, 3 block slots.  Plays the role of the reference's
+ * kernel-selection switch (rys_contract_jk.cu:395-440) for the host-side launch planner. */
+int B200_class_kind(int lp, int lq, int lr, int ls, int row);
 
 /* 1 if a kernel is instantiated with (lp,lq) as the lane side (Y) and (lr,ls)
  * as the register-tile side (X); exactly one orientation of every unordered

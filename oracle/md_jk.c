@@ -500,3 +500,120 @@ void oracle_eri_shell(double *out, const int *atm, const int *bas, const double 
     eri_block(out, get_shell(atm, bas, env, i), get_shell(atm, bas, env, j),
               get_shell(atm, bas, env, k), get_shell(atm, bas, env, l), omega);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * One-electron integrals (overlap S, kinetic T, nuclear attraction V) in the Cartesian AO
+ * basis, McMurchie-Davidson.  Needed only by the TEST-side SCF loop (tests/scf_driver.py) that
+ * checks E_SCF of a GPU J/K build against the CPU one; restates what PySCF's
+ * mol.intor('int1e_ovlp' / 'int1e_kin' / 'int1e_nuc') returns (libcint conventions as above).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Hermite Coulomb integrals R^0_{tuv}(p, PC) for t+u+v <= L */
+static void hermite_R(double *R, int L, double p, double X, double Y, double Z)
+{
+    int n1 = L + 1;
+    double f[4 * LMAX_O + 2];
+    boys(f, L, p * (X * X + Y * Y + Z * Z));
+    /* work[n][t][u][v] */
+    double *w = (double *)calloc((size_t)n1 * n1 * n1 * n1, sizeof(double));
+#define W(n,t,u,v) w[(((n)*n1+(t))*n1+(u))*n1+(v)]
+    double m2p = 1.;
+    for (int n = 0; n <= L; n++) { W(n,0,0,0) = m2p * f[n]; m2p *= -2 * p; }
+    for (int n = L - 1; n >= 0; n--)
+        for (int t = 0; t + n <= L; t++)
+            for (int u = 0; t + u + n <= L; u++)
+                for (int v = 0; t + u + v + n <= L; v++) {
+                    if (t + u + v == 0) continue;
+                    double val;
+                    if (t > 0) val = X * W(n+1,t-1,u,v) + (t > 1 ? (t - 1) * W(n+1,t-2,u,v) : 0.);
+                    else if (u > 0) val = Y * W(n+1,t,u-1,v) + (u > 1 ? (u - 1) * W(n+1,t,u-2,v) : 0.);
+                    else val = Z * W(n+1,t,u,v-1) + (v > 1 ? (v - 1) * W(n+1,t,u,v-2) : 0.);
+                    W(n,t,u,v) = val;
+                }
+    for (int t = 0; t <= L; t++)
+        for (int u = 0; t + u <= L; u++)
+            for (int v = 0; t + u + v <= L; v++) R[(t * n1 + u) * n1 + v] = W(0,t,u,v);
+#undef W
+    free(w);
+}
+
+/* s, t, v: [nao, nao] Cartesian AO matrices (zeroed by the caller) */
+void oracle_int1e(double *s, double *t, double *v, int nao,
+                  const int *atm, int natm, const int *bas, int nbas, const double *env)
+{
+    int *ao_loc = make_ao_loc(bas, nbas);
+    for (int ish = 0; ish < nbas; ish++)
+    for (int jsh = 0; jsh < nbas; jsh++) {
+        Shell si = get_shell(atm, bas, env, ish), sj = get_shell(atm, bas, env, jsh);
+        int li = si.l, lj = sj.l;
+        int cxi[NCART_MAX], cyi[NCART_MAX], czi[NCART_MAX], cxj[NCART_MAX], cyj[NCART_MAX], czj[NCART_MAX];
+        cart_comp(li, cxi, cyi, czi);
+        cart_comp(lj, cxj, cyj, czj);
+        double AB[3] = {si.r[0] - sj.r[0], si.r[1] - sj.r[1], si.r[2] - sj.r[2]};
+        double rr = AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2];
+        int nbj = lj + 3, ntj = li + lj + 4;        /* E arrays up to lj + 2 for the kinetic term */
+        double *E[3];
+        for (int x = 0; x < 3; x++) E[x] = (double *)malloc(sizeof(double) * (li + 1) * nbj * ntj);
+        int L = li + lj;
+        double *R = (double *)malloc(sizeof(double) * (L + 1) * (L + 1) * (L + 1));
+        for (int ip = 0; ip < si.nprim; ip++)
+        for (int jp = 0; jp < sj.nprim; jp++) {
+            double a = si.exps[ip], b = sj.exps[jp], p = a + b;
+            double P[3], pref = exp(-a * b / p * rr) * ang_fac(li) * ang_fac(lj);
+            for (int x = 0; x < 3; x++) {
+                P[x] = (a * si.r[x] + b * sj.r[x]) / p;
+                hermite_E(E[x], li, lj + 2, p, P[x] - si.r[x], P[x] - sj.r[x]);
+            }
+#define EX(x,i,j,tt) E[x][((i)*nbj+(j))*ntj+(tt)]
+            double s3 = pow(M_PI / p, 1.5);
+            for (int ic = 0; ic < si.nctr; ic++)
+            for (int jc = 0; jc < sj.nctr; jc++) {
+                double cc = si.coef[ic * si.nprim + ip] * sj.coef[jc * sj.nprim + jp] * pref;
+                if (cc == 0.) continue;
+                for (int i = 0; i < si.nf; i++)
+                for (int j = 0; j < sj.nf; j++) {
+                    int ix = cxi[i], iy = cyi[i], iz = czi[i], jx = cxj[j], jy = cyj[j], jz = czj[j];
+                    size_t idx = (size_t)(ao_loc[ish] + ic * si.nf + i) * nao + ao_loc[jsh] + jc * sj.nf + j;
+                    double sx = EX(0,ix,jx,0), sy = EX(1,iy,jy,0), sz = EX(2,iz,jz,0);
+                    s[idx] += cc * s3 * sx * sy * sz;
+                    /* kinetic: -1/2 d^2/dx^2 acting on the ket Gaussian */
+                    double kx = -2. * b * b * EX(0,ix,jx+2,0) + b * (2 * jx + 1) * sx
+                              - (jx > 1 ? .5 * jx * (jx - 1) * EX(0,ix,jx-2,0) : 0.);
+                    double ky = -2. * b * b * EX(1,iy,jy+2,0) + b * (2 * jy + 1) * sy
+                              - (jy > 1 ? .5 * jy * (jy - 1) * EX(1,iy,jy-2,0) : 0.);
+                    double kz = -2. * b * b * EX(2,iz,jz+2,0) + b * (2 * jz + 1) * sz
+                              - (jz > 1 ? .5 * jz * (jz - 1) * EX(2,iz,jz-2,0) : 0.);
+                    t[idx] += cc * s3 * (kx * sy * sz + sx * ky * sz + sx * sy * kz);
+                }
+            }
+            /* nuclear attraction: -Z_C * 2 pi / p * sum_tuv E_t E_u E_v R_tuv(p, P - C) */
+            for (int ia = 0; ia < natm; ia++) {
+                double Z = (double)atm[ia * ATM_SLOTS + 0];
+                if (Z == 0.) continue;
+                const double *C = env + atm[ia * ATM_SLOTS + PTR_COORD];
+                hermite_R(R, L, p, P[0] - C[0], P[1] - C[1], P[2] - C[2]);
+                int n1 = L + 1;
+                for (int ic = 0; ic < si.nctr; ic++)
+                for (int jc = 0; jc < sj.nctr; jc++) {
+                    double cc = si.coef[ic * si.nprim + ip] * sj.coef[jc * sj.nprim + jp] * pref;
+                    if (cc == 0.) continue;
+                    for (int i = 0; i < si.nf; i++)
+                    for (int j = 0; j < sj.nf; j++) {
+                        int ix = cxi[i], iy = cyi[i], iz = czi[i], jx = cxj[j], jy = cyj[j], jz = czj[j];
+                        double acc = 0.;
+                        for (int tt = 0; tt <= ix + jx; tt++)
+                        for (int u = 0; u <= iy + jy; u++)
+                        for (int w = 0; w <= iz + jz; w++)
+                            acc += EX(0,ix,jx,tt) * EX(1,iy,jy,u) * EX(2,iz,jz,w) * R[(tt * n1 + u) * n1 + w];
+                        size_t idx = (size_t)(ao_loc[ish] + ic * si.nf + i) * nao + ao_loc[jsh] + jc * sj.nf + j;
+                        v[idx] -= Z * cc * 2. * M_PI / p * acc;
+                    }
+                }
+            }
+#undef EX
+        }
+        for (int x = 0; x < 3; x++) free(E[x]);
+        free(R);
+    }
+    free(ao_loc);
+}

@@ -106,3 +106,32 @@ def q_cond(mol, omega=0.):
                       bas.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(nbas),
                       env.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(omega))
     return q
+
+
+def int1e(mol):
+    """(S, T, V): overlap, kinetic and nuclear-attraction matrices in mol's AO basis -- what
+    mol.intor('int1e_ovlp' / 'int1e_kin' / 'int1e_nuc') returns in PySCF.  Used only by the
+    test-side SCF loop (tests/scf_driver.py)."""
+    lib = _lib()
+    C = _c2s_matrix(mol)
+    nc = C.shape[0]
+    atm = np.ascontiguousarray(mol._atm, dtype=np.int32)
+    bas = np.ascontiguousarray(mol._bas, dtype=np.int32)
+    env = np.ascontiguousarray(mol._env, dtype=np.float64)
+    mats = [np.zeros((nc, nc)) for _ in range(3)]
+    lib.oracle_int1e(*[m.ctypes.data_as(ctypes.c_void_p) for m in mats], ctypes.c_int(nc),
+                     atm.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(atm)),
+                     bas.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(bas)),
+                     env.ctypes.data_as(ctypes.c_void_p))
+    return tuple(C.T @ m @ C for m in mats)
+
+
+def energy_nuc(mol):
+    """nuclear repulsion energy (Hartree)"""
+    z = np.asarray(mol._atm[:, 0], dtype=float)
+    r = mol.atom_coords()
+    e = 0.
+    for i in range(len(z)):
+        for j in range(i):
+            e += z[i] * z[j] / np.linalg.norm(r[i] - r[j])
+    return e

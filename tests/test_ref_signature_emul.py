@@ -58,15 +58,39 @@ vk = vk + vk.transpose(1, 2)
 ref = opt.get_k(dms, 1, omega=omega, lr_factor=lr, sr_factor=sr)
 assert abs(vk - ref).max() < 1e-11, abs(vk - ref).max()
 
-vk0 = torch.zeros_like(dms)
-loop(lambda shls, pij, qij, pkl, qkl: lib.RYS_build_k(
-    jk._ptr(vk0), jk._ptr(dms), 1, naos, 0., 0., 0., ctypes.byref(opt.rys_envs), shls, 0,
+# omega == 0: the weights are scaled by lr_factor (reference: rys_roots_for_k.cu:25-32), so
+# (0, 1, 1) is plain K, (0, .25, .25) a quarter of it and (0, 0, 0) nothing
+def k_at_omega0(fac):
+    out = torch.zeros_like(dms)
+    loop(lambda shls, pij, qij, pkl, qkl: lib.RYS_build_k(
+        jk._ptr(out), jk._ptr(dms), 1, naos, 0., fac, fac, ctypes.byref(opt.rys_envs), shls, 0,
+        len(pij), len(pkl), jk._ptr(pij), jk._ptr(pkl), jk._ptr(qij), jk._ptr(qkl), jk._ptr(qij), jk._ptr(qkl),
+        None, jk._ptr(dm_cond), cutoff, float(dm_cond.max()), jk._ptr(pool),
+        bas_host.ctypes.data_as(ctypes.c_void_p)))
+    return out + out.transpose(1, 2)
+ref0 = opt.get_k(dms, 1)
+assert abs(k_at_omega0(1.) - ref0).max() < 1e-11
+assert abs(k_at_omega0(.25) - .25 * ref0).max() < 1e-11
+assert abs(k_at_omega0(0.)).max() == 0.
+assert abs(opt.get_k(dms, 1, omega=0., lr_factor=.25, sr_factor=.25) - .25 * ref0).max() < 1e-11
+
+# RYS_build_jk with env[8] < 0: short-range J and K (libcint convention), one call per group
+env_host = np.ascontiguousarray(smol._env, dtype=np.float64).copy()
+env_host[8] = -0.35
+vj = torch.zeros_like(dms)
+vk = torch.zeros_like(dms)
+loop(lambda shls, pij, qij, pkl, qkl: lib.RYS_build_jk(
+    jk._ptr(vj), jk._ptr(vk), jk._ptr(dms), 1, naos, ctypes.byref(opt.rys_envs), shls, 0,
     len(pij), len(pkl), jk._ptr(pij), jk._ptr(pkl), jk._ptr(qij), jk._ptr(qkl), jk._ptr(qij), jk._ptr(qkl),
     None, jk._ptr(dm_cond), cutoff, float(dm_cond.max()), jk._ptr(pool),
-    bas_host.ctypes.data_as(ctypes.c_void_p)))
-vk0 = vk0 + vk0.transpose(1, 2)
-ref0 = opt.get_k(dms, 1)
-assert abs(vk0 - ref0).max() < 1e-11, abs(vk0 - ref0).max()
+    bas_host.ctypes.data_as(ctypes.c_void_p), env_host.ctypes.data_as(ctypes.c_void_p)))
+vk = vk + vk.transpose(1, 2)
+vj = 2. * vj
+vj = vj + vj.transpose(1, 2)
+full_j, full_k = opt._jk_pass(dms, 1, True, True, 0.)
+lr_j, lr_k = opt._jk_pass(dms, 1, True, True, 0.35)
+assert abs(vk - (full_k - lr_k)).max() < 1e-11
+assert abs(vj - (full_j - lr_j)).max() < 1e-11
 print('OK')
 ''' % ROOT
 

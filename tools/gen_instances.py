@@ -211,7 +211,7 @@ def main(dst):
                         f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
                                 '{ return jk_launch_thread<%d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
                                 % (name, lp, lq, lr, ls, ndm))
-                        decls.append((lp, lq, lr, ls, ndm, name))
+                        decls.append((lp, lq, lr, ls, ndm, name, 1))
                         continue
                     wc = warp_cfg((lp, lq), (lr, ls), ndm) if WARP_KERNEL else None
                     if wc is not None and (CHOOSER == 'cost' or wc[0] >= 0.3):
@@ -233,12 +233,12 @@ def main(dst):
                             f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
                                     '{ return jk_launch_warp<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
                                     % (name, lp, lq, lr, ls, wc[1], ndm))
-                        decls.append((lp, lq, lr, ls, ndm, name))
+                        decls.append((lp, lq, lr, ls, ndm, name, 2))
                         continue
                     f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
                             '{ return jk_launch<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
                             % (name, lp, lq, lr, ls, ncs, ndm))
-                    decls.append((lp, lq, lr, ls, ndm, name))
+                    decls.append((lp, lq, lr, ls, ndm, name, 3))
     # row-stream instantiations, dealt over the same units
     rdecls = []
     rcls = sorted(row_classes(), key=lambda c: cost(c[:4]), reverse=True)
@@ -250,8 +250,10 @@ def main(dst):
                     f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
                             '{ return jk_launch_rowt<%d, %d, %d, %d, %d>(t, nsm, smem_max, s); }\n'
                             % (name, lp, lq, lr, ls, ndm))
-                    rdecls.append((lp, lq, lr, ls, ndm, name))
+                    rdecls.append((lp, lq, lr, ls, ndm, name, 1))
                     continue
+                if kind == 't':
+                    continue        # thread class whose ndm = 2 form is too fat: two ndm = 1 launches
                 wv = warp_variants(lp, lq, lr, ls, ndm) if WARP_KERNEL else None
                 if wv is None:
                     continue
@@ -265,21 +267,29 @@ def main(dst):
                     f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
                             '{ return jk_launch_warp<%d, %d, %d, %d, %d, %d, 0, 1>(t, nsm, smem_max, s); }\n'
                             % (name, lp, lq, lr, ls, wv[0], ndm))
-                rdecls.append((lp, lq, lr, ls, ndm, name))
+                rdecls.append((lp, lq, lr, ls, ndm, name, 2))
     with open(os.path.join(dst, 'jk_dispatch.inc'), 'w') as f:
         f.write('// GENERATED by tools/gen_instances.py\n')
         for d in rdecls:
             f.write('int %s(JKTask *, int, int, cudaStream_t);\n' % d[5])
         f.write('static jk_launcher_t jk_find_row_launcher(int lp, int lq, int lr, int ls, int ndm)\n{\n'
                 '    switch ((((lp * 8 + lq) * 8 + lr) * 8 + ls) * 4 + ndm) {\n')
-        for (lp, lq, lr, ls, ndm, name) in rdecls:
+        for (lp, lq, lr, ls, ndm, name, kind) in rdecls:
             f.write('    case %d: return %s;\n' % ((((lp * 8 + lq) * 8 + lr) * 8 + ls) * 4 + ndm, name))
         f.write('    }\n    return nullptr;\n}\n')
+        # kernel family of an instantiation: 1 thread per quartet, 2 warp team, 3 block slots
+        f.write('static int jk_class_kind(int lp, int lq, int lr, int ls, int row)\n{\n'
+                '    switch (((((lp * 8 + lq) * 8 + lr) * 8 + ls) * 2) + row) {\n')
+        for row, dl in ((0, decls), (1, rdecls)):
+            for d in dl:
+                if d[4] == 1:
+                    f.write('    case %d: return %d;\n' % ((((d[0] * 8 + d[1]) * 8 + d[2]) * 8 + d[3]) * 2 + row, d[6]))
+        f.write('    }\n    return 0;\n}\n')
         for d in decls:
             f.write('int %s(JKTask *, int, int, cudaStream_t);\n' % d[5])
         f.write('static jk_launcher_t jk_find_launcher(int lp, int lq, int lr, int ls, int ndm)\n{\n'
                 '    switch ((((lp * 8 + lq) * 8 + lr) * 8 + ls) * 4 + ndm) {\n')
-        for (lp, lq, lr, ls, ndm, name) in decls:
+        for (lp, lq, lr, ls, ndm, name, kind) in decls:
             f.write('    case %d: return %s;\n' % ((((lp * 8 + lq) * 8 + lr) * 8 + ls) * 4 + ndm, name))
         f.write('    }\n    return nullptr;\n}\n')
     print(len(cls), 'classes in', NUNITS, 'units')
