@@ -324,11 +324,11 @@ class _VHFOpt:
                     return None
                 # measured on Taxol: it loses against the flat kernels when the streamed shell is a
                 # d shell or higher (long unrolled b loops), and against the thread-per-quartet flat
-                # kernel for the small classes that one serves
+                # kernel where the resident register tile is small (< 18 components)
                 if not force and rl['lq'] >= 2:
                     return None
-                if not force and 1 in (lib.B200_class_kind(*ls(ky), lr, ls_, 0),
-                                       lib.B200_class_kind(lr, ls_, *ls(ky), 0)):
+                if not force and _nf(lr) * _nf(ls_) < 18 and 1 in (lib.B200_class_kind(*ls(ky), lr, ls_, 0),
+                                                                    lib.B200_class_kind(lr, ls_, *ls(ky), 0)):
                     return None
             scattered = _nf(rl['lq']) * (_nf(rl['lp']) + _nf(lr) + _nf(ls_))
             return scattered * (1. + 16. / rl['mean_len'])
