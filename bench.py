@@ -122,6 +122,27 @@ def physical_gpu_index(local):
     return local
 
 
+def workload_config(mol_name, basis, world, extra=None):
+    """`config` of the JSON line -- identical keys and workload string for both arms."""
+    cfg = {'workload': '%s RHF/%s direct-SCF J/K build (hermi=1, n_dm=1, direct_scf_tol=1e-13)' % (mol_name, basis),
+           'density': 'synthetic symmetric, exp(-0.8 R_AB/Bohr) decay + identity (fixed seed; no SCF driver in the '
+                      'product scope, the test-side RHF loop of tests/scf_driver.py covers converged densities)',
+           'n_gpus': world}
+    cfg.update(extra or {})
+    return cfg
+
+
+def committed_counters(mol_name, basis):
+    """Hardware counters of ONE build of this workload summed over all class launches, captured with ncu
+    (tools/ncu_build_counters.py -> profiles/ncu_r2/build_counters_<mol>_<basis>.json).  bench.py cannot read
+    DRAM or SASS counters itself; the file states the command it came from.  None when absent."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_r2', 'build_counters_%s_%s.json' % (mol_name, basis.lower()))
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
 # ----------------------------------------------------------------------
 def cpu_oracle_sample(natoms, basis, mol_name, tol=1e-13):
     '''Time the CPU oracle on the first `natoms` atoms of the workload molecule.
@@ -209,8 +230,8 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 's', 'n_gpus': args.gpus,
         'steps': len(times), 'warmup': 1, 'ms_per_step': v * 1e3, 'higher_is_better': False,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': '%s RHF/%s direct-SCF J/K build (hermi=1, n_dm=1, direct_scf_tol=1e-13)'
-                               % (args.mol, args.basis), 'extrapolated_from_sample': bool(f_full)},
+        'config': workload_config(args.mol, args.basis, args.gpus),
+        'extrapolated_from_sample': bool(f_full),
         'cpu_baseline': {'value': v, 'unit': 's', 'cores': threads, 'kind': 'port', 'sample': sample,
                          'sample_seconds': t, 'sample_gflops': f_c / t / 1e9},
         'e2e': {'value': v, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -318,7 +339,6 @@ def main():
     f_alg_total = float(fl.item())
     kern_ms = sum(a[0] for a in table.values())
     top = max(table.items(), key=lambda kv: kv[1][0])
-    achieved = f_alg_total / (ms_step * 1e-3) / 1e12          # whole build, all ranks
     # the rys class kernels are >99% of the step; "dominant kernel" = the class family
     kern_tf = f_alg / (kern_ms * 1e-3) / 1e12 if kern_ms else 0.
 
@@ -333,31 +353,43 @@ def main():
                                                                      f_alg_total / f_c),
                    'sample_seconds': t, 'sample_gflops': f_c / t / 1e9}
         nbytes = nao * nao * 8
+        # F_hw and DRAM traffic come from a committed ncu capture of the same workload (per build, all launches)
+        ctr = committed_counters(args.mol, args.basis) if world == 1 else None
+        f_hw = ctr.get('f_hw') if ctr else None
+        f_eff = min(f_alg_total, f_hw) if f_hw else f_alg_total
+        achieved = f_eff / (ms_step * 1e-3) / 1e12
+        nominal = 148 * 64 * 2 * 1.965e9 / 1e12                 # 148 SMs x 64 DFMA lanes x 2 flop x 1.965 GHz
         out = {
             'metric': METRIC, 'value': ms_step * 1e-3, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': False,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '%s RHF/%s direct-SCF J/K build (hermi=1, n_dm=1, direct_scf_tol=1e-13)'
-                                   % (args.mol, args.basis),
-                       'nao': nao, 'nao_sorted_cart': nao_s, 'nbas_sorted': opt.sorted_mol.nbas,
-                       'density': 'synthetic symmetric, exp(-0.8 R_AB/Bohr) decay + identity (no SCF driver in scope)',
-                       'parallelism': '(X pair, Y chunk) work items of every class launch dealt round-robin over %d rank(s), one all-reduce of [J|K]' % world,
-                       'l2': 'inputs+outputs (D,J,K = %.0f MB) exceed L2; kernels are FP64-compute bound' % (3 * nao_s * nao_s * 8 / 1e6)},
+            'config': workload_config(args.mol, args.basis, world, {
+                'nao': nao, 'nao_sorted_cart': nao_s, 'nbas_sorted': opt.sorted_mol.nbas,
+                'parallelism': 'work items (X pair, Y chunk / row block) of every class launch dealt round-robin '
+                               'over %d rank(s), one all-reduce of [J|K]' % world,
+                'l2': 'inputs+outputs (D,J,K = %.0f MB) exceed L2; kernels are FP64-compute bound'
+                      % (3 * nao_s * nao_s * 8 / 1e6)}),
             'tflops_fp64': achieved,
             'f_alg': f_alg_total,
+            'f_hw': f_hw,
             'roofline': {'bound': 'fp64_fma', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / (peak * world) if peak else None,
-                         # DRAM bytes of ALL class launches of one build (ncu dram__bytes_read+write summed over the
-                         # 667 launches, profiles/launches_r1_summary.txt); not re-measured live.  Mostly local-memory
-                         # spill traffic of the thread-per-quartet kernels; D, J, K themselves are 155 MB.
-                         'traffic': 79.8e9 if (args.mol, args.basis.lower()) in F_ALG_FULL and world == 1 else None,
-                         'traffic_unit': 'bytes per build, all launches',
+                         'frac_of_nominal': achieved / (nominal * world),
+                         'nominal_peak': nominal,
+                         'achieved_is': 'min(F_alg, F_hw) / t; F_alg = SURVEY 8d flop model x quartets counted by the '
+                                        'kernels in this run, F_hw = 2*DFMA + DMUL + DADD thread instructions of one '
+                                        'build (ncu, committed capture)' if f_hw else
+                                        'F_alg / t (no committed ncu capture for this workload / rank count)',
+                         'traffic': ctr.get('dram_bytes') if ctr else None,
+                         'traffic_unit': 'DRAM bytes per build, all class launches (ncu dram__bytes_read+write)',
+                         'traffic_source': ctr.get('source') if ctr else None,
+                         'algorithmic_bytes': 3 * nao_s * nao_s * 8,
                          'peak_source': 'DFMA burn measured in this run on rank 0 (MEASURED_PEAKS.json has no FP64 figure)',
-                         'kernel': 'rys_jk_kernel / rys_jk_thread_kernel class family (%d launches, %.1f ms of the %.1f ms step on rank 0)'
+                         'kernel': 'rys_jk_{thread,rowt,warp}_kernel class family (%d launches, %.1f ms of the %.1f ms step on rank 0)'
                                    % (nlaunch, kern_ms, ms_step),
-                       'kernel_achieved': kern_tf,
-                       'top_class': {'class': '(%d%d|%d%d)' % top[0], 'ms': top[1][0], 'quartets': top[1][1],
-                                     'tflops': top[1][2] / (top[1][0] * 1e-3) / 1e12 if top[1][0] else None}},
+                         'kernel_achieved': kern_tf,
+                         'top_class': {'class': '(%d%d|%d%d)' % top[0], 'ms': top[1][0], 'quartets': top[1][1],
+                                       'tflops': top[1][2] / (top[1][0] * 1e-3) / 1e12 if top[1][0] else None}},
             'cpu_baseline': cpu,
             'e2e': {'value': ms_e2e * 1e-3, 'unit': 's', 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': 2 * nbytes},
             'gpu_launches': (nlaunch + 1) * args.steps,   # class kernels + condense per build

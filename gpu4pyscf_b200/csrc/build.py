@@ -30,8 +30,14 @@ def _generate(variant=None, genenv=None):
     return gen, sorted(glob.glob(os.path.join(gen, 'jk_inst_*.cu')))
 
 
-def _newest_header():
+# headers only capi.cu includes: a change there does not rebuild the class instantiation units
+CAPI_ONLY = ('qcond.cuh', 'rys_tables.h')
+
+
+def _newest_header(capi=True):
     hs = glob.glob(os.path.join(HERE, '*.cuh')) + glob.glob(os.path.join(HERE, '*.h'))
+    if not capi:
+        hs = [h for h in hs if os.path.basename(h) not in CAPI_ONLY]
     return max(os.path.getmtime(h) for h in hs)
 
 
@@ -47,15 +53,19 @@ def build(emul=False, verbose=False, jobs=None, variant=None, defs=(), genenv=No
         shim = os.path.join(ROOT, 'tests', 'emul')
         srcs = srcs + [os.path.join(shim, 'cuda_shim.cpp')]
         out = os.path.join(shim, 'libgvhf_rys_b200_emul.so')
-        hdr_time = max(_newest_header(), os.path.getmtime(os.path.join(shim, 'cuda_shim.h')))
+        shim_time = os.path.getmtime(os.path.join(shim, 'cuda_shim.h'))
+        hdr_time = max(_newest_header(), shim_time)
+        inst_time = max(_newest_header(False), shim_time)
     else:
         out = os.path.join(ROOT, 'gpu4pyscf_b200', 'lib',
                            'libgvhf_rys_b200%s.so' % ('_' + variant if variant else ''))
         hdr_time = _newest_header()
+        inst_time = _newest_header(False)
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src).rsplit('.', 1)[0] + '.o')
-        if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
+        dep_time = hdr_time if os.path.basename(src) == 'capi.cu' else inst_time
+        if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), dep_time):
             return obj, False
         if emul:
             cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-DCPU_EMUL', '-x', 'c++',

@@ -412,6 +412,89 @@ int B200_qcond(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, i
     return 1;
 }
 
+// Reference signature (nr_sr_estimator.cu:416-430, called from scf/jk.py:1075-1088): Schwarz bounds
+// of the concatenated pair list, block b of the launch owning the pairs
+// [shl_pair_offsets[b], shl_pair_offsets[b+1]) which all belong to one (l_i, l_j, nprim) class.
+// (omega, lr_factor, sr_factor) select the operator exactly as in RYS_build_k.  shm_size and
+// gout_stride_lookup describe the reference kernel's thread layout and are ignored; the value is
+// the FP64 1/2 log max|(ij|ij)| (the reference evaluates the same quantity in FP32 and is tested
+// against libcvhf to 1e-3 log units only, scf/tests/test_scf_jk.py:328-356).
+int int2e_qcond_estimator(float *q_out, RysIntEnvVars *envs, int shm_size,
+                          int nbatches_shl_pair, uint32_t *bas_ij_idx,
+                          int *shl_pair_offsets, int *gout_stride_lookup,
+                          double omega, double lr_factor, double sr_factor)
+{
+    (void)shm_size; (void)gout_stride_lookup;
+    if (nbatches_shl_pair <= 0) return 0;
+    if (RYS_b200_init()) return 1;
+    const int dev = rt_device();
+    double c_full, c_lr;
+    if (omega == 0.) {
+        c_full = lr_factor;
+        c_lr = 0.;
+    } else if (sr_factor == 0.) {
+        c_full = 0.;
+        c_lr = lr_factor;
+    } else {
+        c_full = sr_factor;
+        c_lr = lr_factor - sr_factor;
+    }
+    const double w = omega < 0. ? -omega : omega;
+    // one launch per pair type over all batches: a block returns at once unless its batch has that type
+#define QB(I, J) KLAUNCH((qcond_batch_kernel<I, J>), nbatches_shl_pair, 64, 0, (cudaStream_t)0, q_out, \
+                         (const uint32_t *)bas_ij_idx, (const int *)shl_pair_offsets, (const int *)envs->bas, \
+                         (const double *)envs->env, envs->nbas, (const double *)g_cheb[dev], \
+                         (const double *)g_large[dev], c_full, c_lr, w)
+    QB(0, 0); QB(1, 0); QB(1, 1); QB(2, 0); QB(2, 1); QB(2, 2);
+    QB(3, 0); QB(3, 1); QB(3, 2); QB(3, 3);
+    QB(4, 0); QB(4, 1); QB(4, 2); QB(4, 3); QB(4, 4);
+#undef QB
+    return rt_last_error("qcond_batch_kernel");
+}
+
+// Overlap prescreen + enumeration of the shell pairs ish >= jsh, grouped by group pair
+// gp = gi*(gi+1)/2 + gj (replaces PBCovlp_mask_estimation, lib/pbc/overlap.cu:2236-2260, and
+// PBCsort_pair_ij, lib/pbc/supmol_sr_estimator.cu:461-486, plus the CuPy mask compaction of
+// scf/jk.py:1025-1053).  exps / log_coeff: exponent and log|coefficient| of the most diffuse primitive of
+// every shell (reference: extract_pgto_params, gto/mole.py:348-382); shl_group: group index of every
+// shell; counts: zeroed int[ngroup_pairs].  pairs == NULL: count only; else append every surviving
+// pair id ish*nbas+jsh at offsets[gp] + (running count).
+int B200_pair_prescreen(uint32_t *pairs, int *counts, const int *offsets, const RysIntEnvVars *envs,
+                        const float *exps, const float *log_coeff, const int *shl_group,
+                        float log_cutoff, void *stream)
+{
+    const int nbas = envs->nbas;
+    if (nbas <= 0) return 0;
+    const int nt = 128;
+    const int grid = (int)(((long long)nbas * nbas + nt - 1) / nt);
+    KLAUNCH(pair_prescreen_kernel, grid, nt, 0, (cudaStream_t)stream,
+            pairs, counts, offsets, (const int *)envs->bas, (const double *)envs->env, nbas,
+            exps, log_coeff, shl_group, log_cutoff);
+    return rt_last_error("pair_prescreen_kernel");
+}
+
+// Reference names of the J-only entry (rys_contract_j.cu:824-956, called from scf/jk.py:681-746).
+// The reference kernel works on density / J blocks folded to the (lij+1)(lij+2)(lij+3)/6 "xyz"
+// monomials of every shell pair, a layout produced on the host by its cart2xyz helpers.  Here J-only
+// runs through the same class kernels with a NULL K output on plain (n_dm, nao, nao) matrices in the
+// sorted Cartesian basis, which is what this entry takes: a caller switching to this library skips
+// the two folding transforms (scheme is ignored).
+int RYS_build_j(double *vj, double *dm, int n_dm, int nao,
+                RysIntEnvVars *envs, int *scheme, int *shls_slice,
+                int npairs_ij, int npairs_kl, uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
+                float *q_cond_ij, float *q_cond_kl, float *s_cond_ij, float *s_cond_kl,
+                float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
+                uint32_t *pool, int *bas, double *env)
+{
+    (void)scheme;
+    return RYS_build_jk(vj, nullptr, dm, n_dm, nao, envs, shls_slice, 0, npairs_ij, npairs_kl,
+                        pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl, s_cond_ij, s_cond_kl,
+                        diffuse_exps, dm_cond, cutoff, dm_penalty, pool, bas, env);
+}
+
+// the folded-index tables of the reference's J kernels have no counterpart here
+int RYS_init_rysj_constant(void) { return RYS_b200_init(); }
+
 int B200_pair_rec_stride(int nprim_i, int nprim_j) { return pair_rec_stride(nprim_i * nprim_j); }
 
 int B200_pair_records(double *out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,

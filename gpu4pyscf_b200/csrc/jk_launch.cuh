@@ -11,6 +11,23 @@
 
 typedef int (*jk_launcher_t)(JKTask *t, int nsm, int smem_max, cudaStream_t stream);
 
+// B200_LAUNCH_LOG=1: one stderr line per class launch with its shape and the resources the
+// compiler gave the kernel (tools/launch_table.py joins these with the per-launch times)
+template <class K>
+static inline void jk_log_launch(const char *kind, K kernel, const JKTask *t, int lp, int lq, int lr, int ls,
+                                 int ndm, int nt, int smem, int per_sm, int grid)
+{
+#ifndef CPU_EMUL
+    static const char *on = getenv("B200_LAUNCH_LOG");
+    if (on == nullptr || on[0] != '1') return;
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess) return;
+    fprintf(stderr, "JKLAUNCH %s %d%d%d%d prim %d%d%d%d ndm %d threads %d smem %d blocks_per_sm %d grid %d regs %d stack %d\n",
+            kind, lp, lq, lr, ls, t->nprim_p, t->nprim_q, t->nprim_r, t->nprim_s, ndm, nt, smem, per_sm, grid,
+            a.numRegs, (int)a.localSizeBytes);
+#endif
+}
+
 // Split the Y lists into chunks so that there are enough (X pair, Y chunk) work
 // items for `workers` independent warps/teams; returns the number of items of
 // this rank.
@@ -61,6 +78,7 @@ int jk_launch(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     int grid = nsm * per_sm;
     if (grid > nitems) grid = nitems;
     if (grid < 1) return 0;
+    jk_log_launch("block", rys_jk_kernel<LP, LQ, LR, LS, NCS, NDM>, t, LP, LQ, LR, LS, NDM, nt, smem, per_sm, grid);
     KLAUNCH((rys_jk_kernel<LP, LQ, LR, LS, NCS, NDM>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_kernel");
 }
@@ -89,6 +107,7 @@ int jk_launch_thread(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     int nitems = jk_set_chunks(t, grid * (nt / 32));
     if (grid * (nt / 32) > nitems) grid = (nitems + nt / 32 - 1) / (nt / 32);
     if (grid < 1) return 0;
+    jk_log_launch("thread", rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>, t, LP, LQ, LR, LS, NDM, nt, smem, per_sm, grid);
     KLAUNCH((rys_jk_thread_kernel<LP, LQ, LR, LS, NDM>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_thread_kernel");
 }
@@ -140,7 +159,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     const int rowd = ROW ? 2 * NDM * C::NFP * (C::NFR + C::NFS) : 0;
     auto smem_of = [&](int k) {
         return (RysSmem<C::NROOTS>::DOUBLES
-                + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET, rowd)) * 8;
+                + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET, rowd, C::redd(ROW))) * 8;
     };
     const int budget = (smem_max + 1024) / minb - 1024;
     while (!ROW && K > 1 && smem_of(K) > budget) --K;
@@ -152,7 +171,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         return 1;
     }
     t->nq = K;
-    t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET, rowd);
+    t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET, rowd, C::redd(ROW));
     int per_sm = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL, ROW>, smem, nt);
     if (per_sm < 1) {
         fprintf(stderr, "rys_jk_warp: class (%d%d|%d%d) cannot be made resident (smem %d, threads %d)\n",
@@ -163,6 +182,8 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     long long nitems = ROW ? jk_set_rowblocks(t, grid * nteams) : jk_set_chunks(t, grid * nteams);
     if ((long long)grid * nteams > nitems) grid = (int)((nitems + nteams - 1) / nteams);
     if (grid < 1) return 0;
+    jk_log_launch(ROW ? "roww" : (BL ? "warpbl" : "warp"), rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL, ROW>, t,
+                  LP, LQ, LR, LS, NDM, nt, smem, per_sm, grid);
     KLAUNCH((rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL, ROW>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_warp_kernel");
 }
@@ -190,6 +211,7 @@ int jk_launch_rowt(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     long long nitems = jk_set_rowblocks(t, grid * (nt / 32));
     if ((long long)grid * (nt / 32) > nitems) grid = (int)((nitems + nt / 32 - 1) / (nt / 32));
     if (grid < 1) return 0;
+    jk_log_launch("rowt", rys_jk_rowt_kernel<LP, LQ, LR, LS, NDM>, t, LP, LQ, LR, LS, NDM, nt, smem, per_sm, grid);
     KLAUNCH((rys_jk_rowt_kernel<LP, LQ, LR, LS, NDM>), grid, nt, smem, stream, *t);
     return rt_last_error("rys_jk_rowt_kernel");
 }

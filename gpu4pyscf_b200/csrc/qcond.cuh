@@ -7,18 +7,18 @@
 #include "common.cuh"
 #include "rys_roots.cuh"
 
+// (ij|ij) diagonal of one shell pair for the operator c_full / r + c_lr * erf(omega r) / r
+// (the same two terms as the J/K kernels, reference: rys_roots_for_k.cu:25-60);
+// returns 1/2 log max |(ab|ab)|, -700 for a vanishing pair.
 template <int LI, int LJ>
-__global__ void qcond_kernel(float *q_out, const uint32_t *pairs, int npairs,
-                             const int *bas, const double *env, int nbas,
-                             int nprim_i, int nprim_j,
-                             const double *cheb, const double *large)
+__device__ float qcond_pair(const uint32_t pair, const int *bas, const double *env, const int nbas,
+                            const int nprim_i, const int nprim_j,
+                            const double *cheb, const double *large,
+                            const double c_full, const double c_lr, const double omega)
 {
     constexpr int L2 = LI + LJ;
     constexpr int NROOTS = L2 + 1;
     constexpr int NFI = ncart(LI), NFJ = ncart(LJ);
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= npairs) return;
-    uint32_t pair = pairs[n];
     int ish = pair / nbas;
     int jsh = pair - ish * nbas;
     const double *Ri = env + bas[ish * BAS_SLOTS + PTR_BAS_COORD];
@@ -50,9 +50,23 @@ __global__ void qcond_kernel(float *q_out, const uint32_t *pairs, int npairs,
             double ze = zeta + eta;
             double dx = P[0] - Q[0], dy = P[1] - Q[1], dz = P[2] - Q[2];
             double x = zeta * eta / ze * (dx * dx + dy * dy + dz * dz);
-            double fac = PI_FAC * cij * ckl / (zeta * eta * sqrt(ze));
+            const double fac0 = PI_FAC * cij * ckl / (zeta * eta * sqrt(ze));
+            const double x0 = x;
+            for (int term = 0; term < 2; ++term) {
+            // term 0: c_full / r; term 1: c_lr * erf(omega r) / r (theta -> theta * lrf, rys_roots.cu:91-119)
+            double fac = fac0 * (term == 0 ? c_full : c_lr);
+            if (fac == 0.) continue;
+            double rscale = 1. / ze;
+            x = x0;
+            if (term == 1) {
+                const double theta = zeta * eta / ze;
+                const double lrf = omega * omega / (omega * omega + theta);
+                x *= lrf;
+                rscale *= lrf;
+                fac *= sqrt(lrf);
+            }
             for (int root = 0; root < NROOTS; ++root) {
-                double rt_aa = rys_value<NROOTS>(root, x, cheb, large) / ze;
+                double rt_aa = rys_value<NROOTS>(root, x, cheb, large) * rscale;
                 double w = rys_value<NROOTS>(NROOTS + root, x, cheb, large) * fac;
                 double rt_aij = rt_aa * eta, rt_akl = rt_aa * zeta;
                 double b00 = .5 * rt_aa;
@@ -94,12 +108,98 @@ __global__ void qcond_kernel(float *q_out, const uint32_t *pairs, int npairs,
                                    * diag[1][cart_y(LI, a)][cart_y(LJ, b)]
                                    * diag[2][cart_z(LI, a)][cart_z(LJ, b)];
             }
+            }   // operator terms
         }
     }
     double vmax = 0.;
     for (int a = 0; a < NFI; ++a)
         for (int b = 0; b < NFJ; ++b) vmax = fmax(vmax, fabs(val[a][b]));
-    q_out[n] = vmax > 1e-300 ? (float)(.5 * log(vmax)) : -700.f;
+    return vmax > 1e-300 ? (float)(.5 * log(vmax)) : -700.f;
+}
+
+// one thread per pair of a list of one (li, lj, nprim_i, nprim_j) class
+template <int LI, int LJ>
+__global__ void qcond_kernel(float *q_out, const uint32_t *pairs, int npairs,
+                             const int *bas, const double *env, int nbas,
+                             int nprim_i, int nprim_j,
+                             const double *cheb, const double *large)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npairs) return;
+    q_out[n] = qcond_pair<LI, LJ>(pairs[n], bas, env, nbas, nprim_i, nprim_j, cheb, large, 1., 0., 0.);
+}
+
+// Batched form behind the reference-signature entry int2e_qcond_estimator
+// (nr_sr_estimator.cu:99-131, 416-430): block b owns the pairs
+// [shl_pair_offsets[b], shl_pair_offsets[b+1]) of the concatenated list, all of one
+// (l_i, l_j, nprim_i, nprim_j) class which is read from the batch's first pair, as the
+// reference kernel does.  The <LI, LJ> instantiation serves the batches of its class only.
+template <int LI, int LJ>
+__global__ void qcond_batch_kernel(float *q_out, const uint32_t *bas_ij_idx, const int *shl_pair_offsets,
+                                   const int *bas, const double *env, int nbas,
+                                   const double *cheb, const double *large,
+                                   double c_full, double c_lr, double omega)
+{
+    const int sp0 = shl_pair_offsets[blockIdx.x];
+    const int sp1 = shl_pair_offsets[blockIdx.x + 1];
+    if (sp0 >= sp1) return;
+    const uint32_t first = bas_ij_idx[sp0];
+    const int ish0 = first / nbas;
+    const int jsh0 = first - ish0 * nbas;
+    const int l0 = bas[ish0 * BAS_SLOTS + ANG_OF], l1 = bas[jsh0 * BAS_SLOTS + ANG_OF];
+    // (ij|ij) is symmetric in i <-> j: a batch with l_i < l_j is evaluated as (ji|ji)
+    const bool swap = LI != LJ && l0 == LJ && l1 == LI;
+    if (!swap && (l0 != LI || l1 != LJ)) return;
+    const int nprim_i = bas[(swap ? jsh0 : ish0) * BAS_SLOTS + NPRIM_OF];
+    const int nprim_j = bas[(swap ? ish0 : jsh0) * BAS_SLOTS + NPRIM_OF];
+    for (int n = sp0 + threadIdx.x; n < sp1; n += blockDim.x) {
+        uint32_t pair = bas_ij_idx[n];
+        if (swap) {
+            const uint32_t i = pair / nbas, j = pair - i * nbas;
+            pair = j * nbas + i;
+        }
+        q_out[n] = qcond_pair<LI, LJ>(pair, bas, env, nbas, nprim_i, nprim_j, cheb, large, c_full, c_lr, omega);
+    }
+}
+
+// Overlap prescreen + enumeration of the shell pairs ish >= jsh (reference:
+// ovlp_mask_estimation_kernel, lib/pbc/overlap.cu:2163-2223, and PBCsort_pair_ij,
+// lib/pbc/supmol_sr_estimator.cu:461-486, which produce a mask that CuPy then compacts).
+// Here one kernel does estimate + compaction: every thread owns one (ish, jsh), evaluates the
+// reference's FP32 bound from the most diffuse primitives and, if the pair survives, appends
+// it to the list of its group pair gp = gi*(gi+1)/2 + gj.  Run twice: pairs == NULL counts
+// (counts[gp]), then the fill pass appends at offsets[gp] + atomicAdd(cursor[gp]).  The order
+// inside a group pair is arbitrary; the caller sorts by the Schwarz bound anyway.
+__global__ void pair_prescreen_kernel(uint32_t *pairs, int *counts, const int *offsets,
+                                      const int *bas, const double *env, int nbas,
+                                      const float *exps, const float *log_coeff, const int *shl_group,
+                                      float log_cutoff)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ish = (int)(n / nbas);
+    const int jsh = (int)(n - (long long)ish * nbas);
+    if (ish >= nbas || jsh > ish) return;
+    const int li = bas[ish * BAS_SLOTS + ANG_OF];
+    const int lj = bas[jsh * BAS_SLOTS + ANG_OF];
+    const double *ri = env + bas[ish * BAS_SLOTS + PTR_BAS_COORD];
+    const double *rj = env + bas[jsh * BAS_SLOTS + PTR_BAS_COORD];
+    const float dx = (float)(rj[0] - ri[0]), dy = (float)(rj[1] - ri[1]), dz = (float)(rj[2] - ri[2]);
+    const float ai = exps[ish], aj = exps[jsh];
+    const float aij = ai + aj;
+    const float fi = ai / aij, fj = aj / aij;
+    const float theta = ai * fj;
+    const float rr = dx * dx + dy * dy + dz * dz;
+    if (theta * rr > 50.f) return;                     // REMOTE_THRESHOLD
+    const float dr = sqrtf(rr);
+    const float dri = fj * dr, drj = fi * dr;
+    const float log_ovlp = log_coeff[ish] + log_coeff[jsh] + 1.717f - 1.5f * logf(aij) - theta * rr
+                         + .5f * li * logf(.5f * li / aij + dri * dri + 1e-9f)
+                         + .5f * lj * logf(.5f * lj / aij + drj * drj + 1e-9f);
+    if (!(log_ovlp > log_cutoff)) return;
+    const int gi = shl_group[ish], gj = shl_group[jsh];
+    const int gp = gi * (gi + 1) / 2 + gj;
+    const int pos = atomicAdd(&counts[gp], 1);
+    if (pairs != nullptr) pairs[offsets[gp] + pos] = (uint32_t)ish * nbas + jsh;
 }
 
 // One thread per shell pair: Gaussian-product data of all primitive pairs, so that

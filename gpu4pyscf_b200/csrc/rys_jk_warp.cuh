@@ -36,6 +36,9 @@
 // BL = 1 ("b loop", uncontracted launches only): a lane owns a Cartesian component a of
 // shell p and loops over the nf_q components b itself, so a quartet needs nf_p*NCS lanes
 // instead of nf_p*nf_q*NCS and a warp carries nf_q times more quartets.
+#ifndef JKW_SMEM_RED
+#define JKW_SMEM_RED 1
+#endif
 template <int LP, int LQ, int LR, int LS, int NCS, int BL = 0>
 struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
     typedef JKCfg<LP, LQ, LR, LS, NCS> B;
@@ -125,21 +128,43 @@ struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
         return k;
     }
     static constexpr int KROW = krow();
+    // K rows that several lanes of a single-warp team hold partial sums of -- K_q* over the p
+    // components a, K_p* over the q components b -- are summed through a shared-memory transpose
+    // (REDV values per lane and set, one 32-lane row per value): REDV stores and NFP (NFQ) loads per
+    // quartet instead of REDV * log2(NFP) shuffle + select steps
+    // The scratch (REDV rows of REDS doubles: odd stride, so that the lanes of one column fall in
+    // different banks) is the g-set area of the quartet batch that has just been contracted; only
+    // the b-loop variant, which re-reads its g-sets for the next b, and classes whose batch is
+    // smaller than the scratch get a dedicated buffer.
+    static constexpr int REDV = B::NC + B::NFS;
+    static constexpr int REDS = 33;
+    // Measured on Taxol (profiles/launch_table_r2h_smemred.txt vs launch_table_r2e.txt): the transpose
+    // wins where the shuffle tree is deep and the tile large -- lanes (d,p), (f,s), (f,p) against
+    // (d,d)/(f,d)/(f,f) tiles: -4..-10 % -- and loses 5..20 % for p-shell lanes (two shuffle steps).
+    static constexpr bool RED_WINS = B::NFP >= 10 || (B::NFP >= 6 && B::NFR * B::NFS >= 36);
+    static constexpr bool RED_Q = JKW_SMEM_RED && TW == 1 && B::NFP > 1 && RED_WINS;
+    __host__ __device__ static constexpr bool red_p(int row) { return RED_Q && !row && !BL && B::NFQ > 1; }
+    __host__ __device__ static constexpr int redd(int row)
+    {
+        (void)row;
+        return (RED_Q && (BL || NSW * GSET < REDV * REDS)) ? ((REDV * REDS + 1) & ~1) : 0;
+    }
 };
 
 #define JKW_SLOT_HDR 8       // AB[3], A[3], fac, (p0,q0)
 
 // shared-memory doubles of one team (used by the kernel and by the launcher)
 // rowd: doubles of the row buffers of the row-stream variant (D_p* block + K_p* accumulators), else 0
+// redd: doubles of the reduction scratch (JKWCfg::redd), even
 __host__ __device__ inline int jkw_team_doubles(int team_threads, int nsw, int K, int npq, int nrs,
-                                                int ndm, int nfrs, int gset, int rowd = 0)
+                                                int ndm, int nfrs, int gset, int rowd = 0, int redd = 0)
 {
     int ngs = nsw * K;
     int nqs = (npq * nrs == 1) ? ngs : nsw;
     int qcap = nqs + team_threads;
     int n = 8 + nrs * 5 + ndm * nfrs + rowd + (qcap + 1) / 2 + nqs * (JKW_SLOT_HDR + 5 * npq);
     n = (n + 1) & ~1;                    // g-sets start 16-byte aligned
-    return n + ngs * gset;
+    return n + redd + ngs * gset;
 }
 
 template <int TW>
@@ -264,7 +289,10 @@ rys_jk_warp_kernel(JKTask t)
     double *kpanel = dpx + NDM * NKP;                      // ROW: K_pr | K_ps of the current row
     uint32_t *queue = (uint32_t *)(drs + NDM * NFRS + ROWD);
     double *slots = drs + NDM * NFRS + ROWD + (qcap + 1) / 2;
-    double *gsets = tm + ((8 + nrs * 5 + NDM * NFRS + ROWD + (qcap + 1) / 2 + nqs * slot_d + 1) & ~1);
+    double *red_own = tm + ((8 + nrs * 5 + NDM * NFRS + ROWD + (qcap + 1) / 2 + nqs * slot_d + 1) & ~1);
+    double *gsets = red_own + C::redd(ROW);
+    constexpr bool RED_Q = C::RED_Q, RED_P = C::red_p(ROW);
+    constexpr int REDS = C::REDS;
 
     const int nbas = t.nbas;
     const int nao = t.nao;
@@ -801,6 +829,7 @@ rys_jk_warp_kernel(JKTask t)
             auto digest = [&](double (&gout)[NC][NFS], const int j, const int bb,
                               double (&accp)[NDM][NC], double (&accs)[NDM][NFS], const bool last) {
                 const bool on = lane_on && j < nb;
+                const int jbase = j - s4;             // first quartet slot of this pass
                 int p0 = 0, q0 = 0;
                 if (on) {
                     const int *pi = (const int *)(slots + j * slot_d + 7);
@@ -883,6 +912,115 @@ rys_jk_warp_kernel(JKTask t)
                                 }
                             }
                         }
+                        if (RED_Q) {
+                            // ---- shared-memory transpose reduction: every lane parks its partial K_q* sums
+                            // (and, when they are complete, its K_p* sums); one lane per output row element
+                            // then adds the NFP (NFQ) partials and issues the atomic
+                            const bool stage_p = RED_P && last;
+                            double *red = C::redd(ROW) > 0 ? red_own : gsets + jbase * GSET;
+                            __syncwarp();
+                            if (lane_on) {
+#pragma unroll
+                                for (int n = 0; n < NC; ++n) red[n * REDS + lane] = kqr[n];
+#pragma unroll
+                                for (int d = 0; d < NFS; ++d) red[(NC + d) * REDS + lane] = kqs[d];
+                            }
+                            __syncwarp();
+                            constexpr int NKK = NFR + NFS;
+                            constexpr int NOQ = NSW * NBLANE * NKK;       // K_q* outputs: (slot, b, k)
+                            for (int o = lane; o < NOQ; o += 32) {
+                                const int so = o / (NBLANE * NKK);
+                                const int rem = o - so * (NBLANE * NKK);
+                                const int bo = rem / NKK;
+                                const int k = rem - bo * NKK;
+                                const int jo = jbase + so;
+                                if (jo >= nb) continue;
+                                const int lane0 = so * G + bo * NCS;
+                                double sum = 0., sum1 = 0.;        // two chains: half the dependent adds
+                                if (k < NFR) {
+                                    const int cp = k / NC;
+                                    const double *rp = red + (k - cp * NC) * REDS + lane0 + cp;
+#pragma unroll
+                                    for (int ia = 0; ia + 1 < C::NFP; ia += 2) {
+                                        sum += rp[ia * NBLANE * NCS];
+                                        sum1 += rp[(ia + 1) * NBLANE * NCS];
+                                    }
+                                    if (C::NFP & 1) sum += rp[(C::NFP - 1) * NBLANE * NCS];
+                                } else {
+                                    const double *rp = red + (NC + k - NFR) * REDS + lane0;
+#pragma unroll
+                                    for (int ia = 0; ia < C::NFP; ++ia)
+#pragma unroll
+                                        for (int cp = 0; cp < NCS; ++cp) {
+                                            if ((ia * NCS + cp) & 1) sum1 += rp[ia * NBLANE * NCS + cp];
+                                            else sum += rp[ia * NBLANE * NCS + cp];
+                                        }
+                                }
+                                sum += sum1;
+                                if (sum != 0.) {
+                                    const int qo = ((const int *)(slots + jo * slot_d + 7))[1] + (BL ? bb : bo);
+                                    const int col = k < NFR ? r0 + k : s0 + k - NFR;
+                                    if (ROW) JK_ATOMIC_ADD(t.vkT + idm * nao2 + (size_t)col * nao + qo, sum);
+                                    else JK_ATOMIC_ADD(vk + (size_t)qo * nao + col, sum);
+                                }
+                            }
+                            if (stage_p) {
+                                // same scratch, second round: the completed K_p* partial sums, summed over b
+                                __syncwarp();
+                                if (lane_on) {
+#pragma unroll
+                                    for (int n = 0; n < NC; ++n) red[n * REDS + lane] = accp[idm][n];
+#pragma unroll
+                                    for (int d = 0; d < NFS; ++d) red[(NC + d) * REDS + lane] = accs[idm][d];
+                                }
+                                __syncwarp();
+                                constexpr int NOP = NSW * C::NFP * NKK;   // K_p* outputs: (slot, a, k)
+                                for (int o = lane; o < NOP; o += 32) {
+                                    const int so = o / (C::NFP * NKK);
+                                    const int rem = o - so * (C::NFP * NKK);
+                                    const int ao = rem / NKK;
+                                    const int k = rem - ao * NKK;
+                                    const int jo = jbase + so;
+                                    if (jo >= nb) continue;
+                                    const int lane0 = so * G + ao * NFQ * NCS;
+                                    double sum = 0., sum1 = 0.;
+                                    if (k < NFR) {
+                                        const int cp = k / NC;
+                                        const double *rp = red + (k - cp * NC) * REDS + lane0 + cp;
+#pragma unroll
+                                        for (int ib = 0; ib + 1 < NFQ; ib += 2) {
+                                            sum += rp[ib * NCS];
+                                            sum1 += rp[(ib + 1) * NCS];
+                                        }
+                                        if (NFQ & 1) sum += rp[(NFQ - 1) * NCS];
+                                    } else {
+                                        const double *rp = red + (NC + k - NFR) * REDS + lane0;
+#pragma unroll
+                                        for (int ib = 0; ib < NFQ; ++ib)
+#pragma unroll
+                                            for (int cp = 0; cp < NCS; ++cp) {
+                                                if ((ib * NCS + cp) & 1) sum1 += rp[ib * NCS + cp];
+                                                else sum += rp[ib * NCS + cp];
+                                            }
+                                    }
+                                    sum += sum1;
+                                    if (sum != 0.) {
+                                        const int po = ((const int *)(slots + jo * slot_d + 7))[0] + ao;
+                                        const int col = k < NFR ? r0 + k : s0 + k - NFR;
+                                        JK_ATOMIC_ADD(vk + (size_t)po * nao + col, sum);
+                                    }
+                                }
+                            } else if (last && !ROW) {
+                                // b-loop variant or s-type q shell: the K_p* rows are complete in the lane
+                                if (on) {
+#pragma unroll
+                                    for (int n = 0; n < NC; ++n)
+                                        if (c0 + n < NFR) JK_ATOMIC_ADD(vk + prow + r0 + c0 + n, accp[idm][n]);
+#pragma unroll
+                                    for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + prow + s0 + d, accs[idm][d]);
+                                }
+                            }
+                        } else {
                         // K_q* rows: sum over a across lanes, one atomic from the a == 0 lane
                         bool lead_q = true;
                         if (SHFL_RED && C::NFP > 1) {
@@ -927,6 +1065,7 @@ rys_jk_warp_kernel(JKTask t)
                                 for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + prow + s0 + d, accs[idm][d]);
                             }
                         }
+                        }   // !RED_Q
                     }
                 }
             };

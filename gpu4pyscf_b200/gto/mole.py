@@ -282,6 +282,9 @@ def _scale_sp_ctr_coeff(mol):
     return env
 
 
+MAX_NPRIM = 6        # primitives per sorted shell (csrc/jk_launch.cuh: JK_MAXPP = 36 primitive pairs)
+
+
 class SortedGTO:
     """Decontracted, (l, nprim)-sorted Cartesian view of a ``Mole``.
 
@@ -316,6 +319,9 @@ class SortedGTO:
                 else:
                     groups = ([np.where(~diffuse)[0]] if (~diffuse).any() else []) + \
                              [np.array([i]) for i in np.where(diffuse)[0]]
+                # the kernels hold at most 36 primitive pairs of a shell pair (JK_MAXPP): longer
+                # segmented contractions are cut into pieces of <= 6 primitives whose functions add up
+                groups = [g[i:i + MAX_NPRIM] for g in groups for i in range(0, len(g), MAX_NPRIM)]
                 for g in groups:
                     env.append(es[g])
                     env.append(cs[0, g])

@@ -77,6 +77,16 @@ def load_library(name='libgvhf_rys_b200'):
         vp, vp, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp]
     lib.B200_qcond.restype = c_int
     lib.B200_qcond.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.int2e_qcond_estimator.restype = c_int
+    lib.int2e_qcond_estimator.argtypes = [vp, vp, c_int, c_int, vp, vp, vp,
+                                          ctypes.c_double, ctypes.c_double, ctypes.c_double]
+    lib.B200_pair_prescreen.restype = c_int
+    lib.B200_pair_prescreen.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_float, vp]
+    lib.RYS_build_j.restype = c_int
+    lib.RYS_build_j.argtypes = [
+        vp, vp, c_int, c_int, vp, vp, vp, c_int, c_int,
+        vp, vp, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp, vp]
+    lib.RYS_init_rysj_constant.restype = c_int
     lib.B200_set_counter.restype = c_int
     lib.B200_set_counter.argtypes = [vp]
     lib.B200_condense.restype = c_int

@@ -558,57 +558,106 @@ class _VHFOpt:
         return self._qmax_cache
 
 
+def _diffuse_pgto_params(smol):
+    '''Exponent and |coefficient| of the most diffuse primitive of every (sorted) shell, picked
+    like the reference's extract_pgto_params(mol, 'diffuse') (gto/mole.py:348-382).'''
+    exps = np.empty(smol.nbas, dtype=np.float32)
+    cs = np.empty(smol.nbas, dtype=np.float32)
+    precision = 1e-8
+    for ib, b in enumerate(smol._bas):
+        l, nprim, nctr = int(b[ANG_OF]), int(b[NPRIM_OF]), int(b[3])
+        e = smol._env[b[5]:b[5] + nprim]
+        c = np.abs(smol._env[b[6]:b[6] + nprim * nctr].reshape(nctr, nprim)).max(axis=0)
+        tmp = (2 * l + 1) / (4 * np.pi) / precision**2 * c**2 * 1e2**l
+        tmp[tmp <= 0] = 1e-200
+        k = int(np.argmax(np.log(tmp) / (2 * e)))
+        exps[ib], cs[ib] = e[k], c[k]
+    return exps, cs
+
+
 def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib, q_bin=0.):
-    '''Per group pair (gi >= gj): shell-pair ids ``ish*nbas+jsh`` (ish >= jsh),
-    their Schwarz bounds q = 1/2 log max|(ij|ij)| and the same again as
-    ``s_cond`` -- each list sorted by q descending (exactly; the reference bins
-    by 4 log-units, jk.py:984-1120).  Pairs that cannot survive against the
-    largest bound of the molecule are dropped.'''
+    '''Per group pair (gi >= gj): shell-pair ids ``ish*nbas+jsh`` (ish >= jsh), their Schwarz
+    bounds q = 1/2 log max|(ij|ij)|, the same again as ``s_cond`` and the Gaussian-product
+    records -- same role and call sequence as the reference (scf/jk.py:984-1120):
+
+    1. overlap prescreen + enumeration of all ish >= jsh pairs in one kernel
+       (``B200_pair_prescreen``: count pass, prefix sum, fill pass),
+    2. ONE ``int2e_qcond_estimator`` launch sequence over the concatenated list (reference signature),
+    3. one global sort by (group pair, q bin descending, pair id) -- the reference bins by 4 log
+       units (Q_COND_MARGIN); here the bins are ``q_bin`` wide (0: exactly q-sorted), and pairs
+       that cannot survive against the largest bound of the molecule are dropped,
+    4. one ``B200_pair_records`` launch per group pair.'''
     nbas = smol.nbas
     uniq = smol.uniq_l_ctr
     counts = np.asarray(smol.l_ctr_counts)
-    offs = np.append(0, np.cumsum(counts))
     ngroups = len(counts)
+    ngp = ngroups * (ngroups + 1) // 2
     log_cutoff = math.log(precision)
     stream = loader.current_stream_ptr()
-    raw = {}
-    for gi in range(ngroups):
-        for gj in range(gi + 1):
-            ish = torch.arange(offs[gi], offs[gi + 1], device=device, dtype=torch.int64)
-            jsh = torch.arange(offs[gj], offs[gj + 1], device=device, dtype=torch.int64)
-            ii, jj = torch.meshgrid(ish, jsh, indexing='ij')
-            ids = (ii * nbas + jj).reshape(-1)
-            if gi == gj:
-                ids = ids[(ii >= jj).reshape(-1)]
-            ids = ids.to(torch.int32).contiguous()
-            q = torch.empty(len(ids), dtype=torch.float32, device=device)
-            err = lib.B200_qcond(_ptr(q), ctypes.byref(rys_envs), _ptr(ids), len(ids),
-                                 int(uniq[gi, 0]), int(uniq[gj, 0]),
-                                 int(uniq[gi, 1]), int(uniq[gj, 1]), stream)
-            if err:
-                raise RuntimeError('B200_qcond failed')
-            raw[gi, gj] = (ids, q)
-    qmax = max(float(q.max()) for _, q in raw.values() if len(q))
+    i32 = dict(dtype=torch.int32, device=device)
+
+    exps, cs = _diffuse_pgto_params(smol)
+    exps_d = torch.as_tensor(exps, device=device)
+    logc_d = torch.as_tensor(np.log(np.maximum(cs, 1e-30)).astype(np.float32), device=device)
+    grp_d = torch.as_tensor(np.repeat(np.arange(ngroups), counts).astype(np.int32), device=device)
+    cnt_d = torch.zeros(ngp, **i32)
+    args = (ctypes.byref(rys_envs), _ptr(exps_d), _ptr(logc_d), _ptr(grp_d), 2. * log_cutoff, stream)
+    if lib.B200_pair_prescreen(None, _ptr(cnt_d), None, *args):
+        raise RuntimeError('B200_pair_prescreen failed')
+    cnt = cnt_d.cpu().numpy().astype(np.int64)
+    offs = np.append(0, np.cumsum(cnt))
+    ntot = int(offs[-1])
+    keys = [(gi, gj) for gi in range(ngroups) for gj in range(gi + 1)]
+    if ntot == 0:
+        empty = torch.zeros(0, **i32)
+        emptyq = torch.zeros(0, dtype=torch.float32, device=device)
+        return {k: (empty, emptyq, emptyq, torch.zeros(0, dtype=torch.float64, device=device)) for k in keys}
+    offs_d = torch.as_tensor(offs[:-1].astype(np.int32), device=device)
+    ids = torch.empty(ntot, **i32)
+    cnt_d.zero_()
+    if lib.B200_pair_prescreen(_ptr(ids), _ptr(cnt_d), _ptr(offs_d), *args):
+        raise RuntimeError('B200_pair_prescreen failed')
+
+    # batches of one launch block each; no batch crosses a group-pair boundary
+    batch = 256
+    spo = np.hstack([np.arange(offs[g], offs[g + 1], batch) for g in range(ngp)] + [[ntot]]).astype(np.int32)
+    spo_d = torch.as_tensor(spo, device=device)
+    q = torch.empty(ntot, dtype=torch.float32, device=device)
+    # the estimator runs on the legacy default stream, like the reference's
+    if device.type == 'cuda':
+        torch.cuda.current_stream().synchronize()
+    if lib.int2e_qcond_estimator(_ptr(q), ctypes.byref(rys_envs), 0, len(spo) - 1, _ptr(ids), _ptr(spo_d),
+                                 None, 0., 1., 1.):
+        raise RuntimeError('int2e_qcond_estimator kernel failed')
+    if device.type == 'cuda':
+        torch.cuda.synchronize()
+
+    gp = torch.repeat_interleave(torch.arange(ngp, device=device), torch.as_tensor(cnt, device=device))
+    keep = q + q.max() > log_cutoff
+    ids, q, gp = ids[keep], q[keep], gp[keep]
+    ids64 = ids.to(torch.int64)
+    if q_bin > 0:
+        # descending q bins of width q_bin, shell-pair order (ish, jsh) inside a bin: neighbours in the
+        # list share the bra shell, so the D rows they load and the K rows they update coincide
+        # (the kernels get q_margin = q_bin for the early exit)
+        bins = torch.floor(q.double() / q_bin).to(torch.int64)
+        bins = bins.max() - bins
+        order = torch.argsort((gp * (int(bins.max()) + 1) + bins) * (int(nbas) * int(nbas)) + ids64)
+    else:
+        order = torch.argsort(q, descending=True, stable=True)
+        order = order[torch.argsort(gp[order], stable=True)]
+    ids = ids[order].contiguous()
+    q = q[order].contiguous()
+    kept = torch.bincount(gp, minlength=ngp).cpu().numpy()
+    koffs = np.append(0, np.cumsum(kept))
     cache = {}
-    for key, (ids, q) in raw.items():
-        keep = q + qmax > log_cutoff
-        ids, q = ids[keep], q[keep]
-        if q_bin > 0:
-            # descending q bins of width q_bin, shell-pair order (ish, jsh) inside a bin:
-            # neighbours in the list share the bra shell, so the D rows they load and the
-            # K rows they update coincide (the kernels get q_margin = q_bin for the early exit)
-            bins = torch.floor(q.double() / q_bin).to(torch.int64)
-            order = torch.argsort((bins.max() - bins) * (int(nbas) * int(nbas)) + ids.to(torch.int64)) \
-                if len(q) else torch.zeros(0, dtype=torch.int64, device=device)
-        else:
-            order = torch.argsort(q, descending=True, stable=True)
-        ids = ids[order].contiguous()
-        q = q[order].contiguous()
+    for g, key in enumerate(keys):
+        a, b = int(koffs[g]), int(koffs[g + 1])
+        ids_g, q_g = ids[a:b], q[a:b]
         # Gaussian-product records of the pairs, in list order
         npi, npj = int(uniq[key[0], 1]), int(uniq[key[1], 1])
-        rec = torch.empty(len(ids) * lib.B200_pair_rec_stride(npi, npj), dtype=torch.float64, device=device)
-        err = lib.B200_pair_records(_ptr(rec), ctypes.byref(rys_envs), _ptr(ids), len(ids), npi, npj, stream)
-        if err:
+        rec = torch.empty((b - a) * lib.B200_pair_rec_stride(npi, npj), dtype=torch.float64, device=device)
+        if b > a and lib.B200_pair_records(_ptr(rec), ctypes.byref(rys_envs), _ptr(ids_g), b - a, npi, npj, stream):
             raise RuntimeError('B200_pair_records failed')
-        cache[key] = (ids, q, q, rec)
+        cache[key] = (ids_g, q_g, q_g, rec)
     return cache

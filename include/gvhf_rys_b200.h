@@ -154,6 +154,45 @@ int B200_pair_records(double *out, const RysIntEnvVars *envs, const uint32_t *pa
 int B200_qcond(float *q_out, const RysIntEnvVars *envs, const uint32_t *pairs, int npairs,
                int li, int lj, int nprim_i, int nprim_j, void *stream);
 
+/* Reference signature: int2e_qcond_estimator, lib/gvhf-rys/nr_sr_estimator.cu:416-430, called from
+ * gpu4pyscf/scf/jk.py:1075-1088.  q_out[n] = 1/2 log max|(ij|ij)| for the concatenated pair list
+ * bas_ij_idx; block b of the launch owns [shl_pair_offsets[b], shl_pair_offsets[b+1]), all of one
+ * (l_i, l_j, nprim_i, nprim_j) class (read from the batch's first pair, as in the reference).
+ * (omega, lr_factor, sr_factor): operator lr_factor*erf(|omega| r)/r + sr_factor*erfc(|omega| r)/r with
+ * the rules of RYS_build_k.  shm_size and gout_stride_lookup are accepted and ignored.  Legacy
+ * default stream, like the reference. */
+int int2e_qcond_estimator(float *q_out, RysIntEnvVars *envs, int shm_size,
+                          int nbatches_shl_pair, uint32_t *bas_ij_idx,
+                          int *shl_pair_offsets, int *gout_stride_lookup,
+                          double omega, double lr_factor, double sr_factor);
+
+/* Overlap prescreen + enumeration of the shell pairs ish >= jsh in one kernel.  Replaces
+ * PBCovlp_mask_estimation (lib/pbc/overlap.cu:2163-2260), PBCsort_pair_ij
+ * (lib/pbc/supmol_sr_estimator.cu:461-486) and the CuPy mask compaction of scf/jk.py:1025-1053.
+ *   exps, log_coeff  float[nbas]: exponent and log|coefficient| of the most diffuse primitive of each shell
+ *   shl_group        int[nbas]: (l, nprim) group of each shell; group pair gp = gi*(gi+1)/2 + gj
+ *   counts           zeroed int[ngroups*(ngroups+1)/2]: receives the number of surviving pairs per gp
+ *   pairs == NULL    count only; otherwise pair ids ish*nbas+jsh are appended at offsets[gp] + running count
+ *   log_cutoff       log(precision^2), as the reference passes (scf/jk.py:1025). */
+int B200_pair_prescreen(uint32_t *pairs, int *counts, const int *offsets, const RysIntEnvVars *envs,
+                        const float *exps, const float *log_coeff, const int *shl_group,
+                        float log_cutoff, void *stream);
+
+/* Reference names of the J-only entry: RYS_build_j / RYS_init_rysj_constant,
+ * lib/gvhf-rys/rys_contract_j.cu:824-956, called from gpu4pyscf/scf/jk.py:681-746.  DIFFERENCE: the
+ * reference kernel takes density and J blocks folded to the xyz monomials of every shell pair (its
+ * host-side cart2xyz layout, described by `scheme`); this entry takes plain (n_dm, nao, nao)
+ * matrices in the sorted Cartesian basis and runs the J/K class kernels with a NULL K output, so a
+ * caller that switches libraries drops the two folding transforms.  `scheme` is ignored.
+ * Everything else (group slices, pair lists, de-duplication, env[8] = omega) as RYS_build_jk. */
+int RYS_build_j(double *vj, double *dm, int n_dm, int nao,
+                RysIntEnvVars *envs, int *scheme, int *shls_slice,
+                int npairs_ij, int npairs_kl, uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping,
+                float *q_cond_ij, float *q_cond_kl, float *s_cond_ij, float *s_cond_kl,
+                float *diffuse_exps, float *dm_cond, float cutoff, float dm_penalty,
+                uint32_t *pool, int *bas, double *env);
+int RYS_init_rysj_constant(void);
+
 /* dm_cond[i*nbas+j] = log(max |D_n[a,b]| + 1e-300) over the AO block of shell
  * pair (i,j) and all n_dm matrices.  Replaces the CuPy RawKernel behind
  * condense('absmax', ...) (gpu4pyscf/lib/cupy_helper.py:1068-1184, used at

@@ -91,6 +91,44 @@ full_j, full_k = opt._jk_pass(dms, 1, True, True, 0.)
 lr_j, lr_k = opt._jk_pass(dms, 1, True, True, 0.35)
 assert abs(vk - (full_k - lr_k)).max() < 1e-11
 assert abs(vj - (full_j - lr_j)).max() < 1e-11
+
+# RYS_build_j (reference name; plain sorted-Cartesian matrices, see include/gvhf_rys_b200.h)
+assert lib.RYS_init_rysj_constant() == 0
+env_host[8] = 0.
+vj = torch.zeros_like(dms)
+loop(lambda shls, pij, qij, pkl, qkl: lib.RYS_build_j(
+    jk._ptr(vj), jk._ptr(dms), 1, naos, ctypes.byref(opt.rys_envs), None, shls,
+    len(pij), len(pkl), jk._ptr(pij), jk._ptr(pkl), jk._ptr(qij), jk._ptr(qkl), jk._ptr(qij), jk._ptr(qkl),
+    None, jk._ptr(dm_cond), cutoff, float(dm_cond.max()), jk._ptr(pool),
+    bas_host.ctypes.data_as(ctypes.c_void_p), env_host.ctypes.data_as(ctypes.c_void_p)))
+vj = 2. * vj
+vj = vj + vj.transpose(1, 2)
+assert abs(vj - opt.get_j(dms)).max() < 1e-11
+
+# int2e_qcond_estimator (reference signature) for the three operators against the oracle's
+# sqrt(max|(ij|ij)|): full range, long range (omega > 0, sr = 0), short range (omega < 0, lr = 0)
+from oracle import oracle
+ids = torch.cat([v[0] for v in opt.bas_pair_cache.values()]).contiguous()
+cnts = [len(v[0]) for v in opt.bas_pair_cache.values()]
+o = np.append(0, np.cumsum(cnts))
+spo = torch.as_tensor(np.hstack([np.arange(o[g], o[g + 1], 7) for g in range(len(cnts))] + [[o[-1]]]).astype(np.int32))
+idn = ids.numpy().astype(np.int64)
+for om, lrf, srf in ((0., 1., 1.), (0.4, 1., 0.), (-0.4, 0., 1.)):
+    q = torch.empty(len(ids), dtype=torch.float32)
+    assert lib.int2e_qcond_estimator(jk._ptr(q), ctypes.byref(opt.rys_envs), 0, len(spo) - 1, jk._ptr(ids),
+                                     jk._ptr(spo), None, om, lrf, srf) == 0
+    ref = np.log(oracle.q_cond(smol, omega=om)[idn // nbas, idn %% nbas])
+    assert abs(q.numpy() - ref).max() < 2e-5, (om, abs(q.numpy() - ref).max())
+
+# pair prescreen: the group-pair lists hold exactly the ish >= jsh pairs of their two groups, once each
+seen = set()
+grp = np.repeat(np.arange(ng), smol.l_ctr_counts)
+for (gi, gj), v in opt.bas_pair_cache.items():
+    a = v[0].numpy().astype(np.int64)
+    assert (grp[a // nbas] == gi).all() and (grp[a %% nbas] == gj).all() and (a // nbas >= a %% nbas).all()
+    assert len(set(a.tolist())) == len(a) and not (seen & set(a.tolist()))
+    seen |= set(a.tolist())
+assert len(seen) == nbas * (nbas + 1) // 2          # water: nothing is far enough to be dropped
 print('OK')
 ''' % ROOT
 

@@ -61,7 +61,13 @@ BL_ENABLE = os.environ.get('B200_BL', '1') == '1'
 BL_GAIN = float(os.environ.get('B200_BL_GAIN', '0.85'))   # use the b-loop variant when its modelled cost is below this fraction
 
 
-def warp_cfg_cost(y, x, ndm, bl=False):
+# register budget (doubles) of the b-loop variant in ROW kernels.  Measured on Taxol (round 2):
+# raising it so that (21|32) / (11|32) rows take the b-loop variant (5 quartets per warp instead of
+# 1 or 3) LOSES -- 147 vs 143 ms and 60 vs 43 ms: one g-set per lane slot and 7 instead of 8 warps/SM
+BL_ROW_REG = int(os.environ.get('B200_BL_ROW_REG', str(REG_DOUBLES)))
+
+
+def warp_cfg_cost(y, x, ndm, bl=False, row=False):
     """Instruction-count model: estimated warp instructions per quartet for lanes =
     Y pair, register tile = X pair (split NCS ways); returns (-cost, ncs) so that
     larger is better, like warp_cfg."""
@@ -86,7 +92,7 @@ def warp_cfg_cost(y, x, ndm, bl=False):
         nsw = 32 // g if tw == 1 else 1
         seg = lrs + 1 if ncs == 1 else sub
         regs = tile * (1 + ndm) + (3 * sub + 3 * seg if ncs == 1 else 3 * (ls + 1)) + (bl and (nc + nfs) * ndm)
-        if regs > REG_DOUBLES:
+        if regs > (BL_ROW_REG if bl and row else REG_DOUBLES):
             continue
         ld = 3 * ((seg + 1) // 2) if ncs == 1 else 3 * (ls + 1) * nc
         hrr = 3 * sum(lrs - d for d in range(ls)) if ncs == 1 else 0
@@ -176,13 +182,13 @@ def row_classes():
 
 
 def warp_variants(lp, lq, lr, ls, ndm):
-    """(ncs of the general kernel, ncs of the b-loop variant or None)"""
+    """(ncs of the general kernel, ncs of the b-loop variant or None) of a ROW class"""
     wc = warp_cfg((lp, lq), (lr, ls), ndm)
     if wc is None:
         return None
     bl = None
     if BL_ENABLE and CHOOSER == 'cost' and lq > 0:
-        bl = warp_cfg_cost((lp, lq), (lr, ls), ndm, bl=True)
+        bl = warp_cfg_cost((lp, lq), (lr, ls), ndm, bl=True, row=True)
         # measured on Taxol: pays off for unsplit register tiles only
         if bl is not None and (-bl[0] > BL_GAIN * -wc[0] or bl[1] != 1):
             bl = None
