@@ -20,6 +20,7 @@ summed with ONE ``all_reduce`` per build.
 import ctypes
 import math
 import os
+import time
 import numpy as np
 import torch
 
@@ -149,6 +150,24 @@ def _nf(l):
     return (l + 1) * (l + 2) // 2
 
 
+def _lpt_owners(cost, world, split_min=float('inf')):
+    '''Longest-processing-time-first assignment of launches to ranks: heaviest launch first, each to
+    the least loaded rank (ties by index, so every rank derives the same table).  Launches of cost
+    >= split_min get owner -1: their work items are dealt over all ranks instead.  Plays the role of
+    the reference's dynamic per-device task hand-out (lib/multi_gpu.py:126-206, jk.py:520-524).'''
+    order = sorted(range(len(cost)), key=lambda i: (-cost[i], i))
+    load = [0.] * world
+    owners = [0] * len(cost)
+    for i in order:
+        if cost[i] >= split_min:
+            owners[i] = -1
+            continue
+        r = min(range(world), key=lambda k: (load[k], k))
+        owners[i] = r
+        load[r] += cost[i]
+    return owners
+
+
 class _VHFOpt:
     '''Screening object of the direct-SCF J/K build (reference: jk.py:407-927).'''
 
@@ -176,6 +195,7 @@ class _VHFOpt:
         self._tasks = None
         self._qmax_cache = None
         self._rows = {}
+        self._launch_cost = None      # measured GPU ms per class launch (multi-GPU cost partition)
 
     def reset(self, mol):
         self.mol = mol
@@ -185,6 +205,7 @@ class _VHFOpt:
         self._tasks = None
         self._qmax_cache = None
         self._rows = {}
+        self._launch_cost = None
         return self
 
     # ------------------------------------------------------------------
@@ -205,6 +226,7 @@ class _VHFOpt:
             smol, self._rys_envs, self.direct_scf_tol, self.device, lib, self.q_bin)
         self._rows = {}
         self._tasks = None
+        self._launch_cost = None
         return self
 
     def _make_rys_envs(self):
@@ -394,7 +416,26 @@ class _VHFOpt:
         nj = ndm_k if with_j else 0
         nk = ndm_k if with_k else 0
         nt = ndm_k if sep_kT else 0
-        out = torch.zeros((nj + nk + nt, nao, nao), dtype=torch.float64, device=dev)
+        rank, world = self._partition()
+        # Multi-GPU partition (B200_PARTITION).  'items': the work items (X pair, Y chunk / row block) of every
+        # launch are dealt round-robin over the ranks -- balanced by construction, but a launch that lasts
+        # < 1 ms on 8 GPUs pays its fixed costs (launch gap, table staging, tail) on every rank.
+        # 'hybrid' (default): launches whose measured GPU time is below B200_SPLIT_MIN_MS run WHOLE on one rank,
+        # assigned longest-processing-time-first; the heavy launches stay item-dealt.  'cost': every launch
+        # whole on one rank (measured on 8 B200: 0.735 s vs 0.684 s for 'items' -- the measured costs of the
+        # heavy launches are not accurate enough to balance them).  The first build of a _VHFOpt measures the
+        # launch times (items dealt, launches serialised, CUDA events) and ships them in the tail of the
+        # [vj|vk] buffer, so there is still ONE all_reduce per build.
+        part = os.environ.get('B200_PARTITION', 'hybrid')
+        cost_mode = world > 1 and part in ('cost', 'hybrid') and self.class_timing is None
+        measuring = cost_mode and (self._launch_cost is None or len(self._launch_cost) != len(tasks))
+        owners = None
+        if cost_mode and not measuring:
+            split_min = float(os.environ.get('B200_SPLIT_MIN_MS', '20')) if part == 'hybrid' else float('inf')
+            owners = _lpt_owners(self._launch_cost, world, split_min)
+        nmat = nj + nk + nt
+        flat = torch.zeros(nmat * nao * nao + (len(tasks) if measuring else 0), dtype=torch.float64, device=dev)
+        out = flat[:nmat * nao * nao].view(nmat, nao, nao)
         vj = out[:nj] if with_j else None
         vk = out[nj:nj + nk] if with_k else None
         vkT = out[nj + nk:] if sep_kT else vk
@@ -403,7 +444,7 @@ class _VHFOpt:
         # they are dealt over a few side streams: the tail of one launch, when
         # most SMs have run out of work items, overlaps the start of the next.
         side = None
-        if dev.type == 'cuda' and self.class_timing is None and self.n_streams > 1:
+        if dev.type == 'cuda' and self.class_timing is None and self.n_streams > 1 and not measuring:
             if self._streams is None:
                 self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams)]
             side = self._streams
@@ -424,9 +465,9 @@ class _VHFOpt:
             ev.record(main)
             for st in side:
                 st.wait_event(ev)
-        rank, world = self._partition()
         uniq = smol.uniq_l_ctr
         lprim = (ctypes.c_int * 8)()
+        timers = []
         only = getattr(self, 'only_classes', None)   # measurement: restrict to some classes
         for it, (mode, ky, kx, dedupe) in enumerate(tasks):
             pair_x, q_x = self.bas_pair_cache[kx][:2]
@@ -447,6 +488,18 @@ class _VHFOpt:
                 if tuple(lprim[:4]) not in only and tuple(lprim) not in only:
                     continue
             head = ctypes.c_void_p(heads.data_ptr() + 8 * it)
+            l_rank, l_world = rank, world
+            if owners is not None and owners[it] >= 0:
+                if owners[it] != rank:
+                    continue
+                l_rank, l_world = 0, 1
+            if measuring:
+                if dev.type == 'cuda':
+                    tm0 = torch.cuda.Event(enable_timing=True)
+                    tm1 = torch.cuda.Event(enable_timing=True)
+                    tm0.record()
+                else:
+                    tm0 = time.perf_counter()
             if self.class_timing is not None and dev.type == 'cuda':
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev1 = torch.cuda.Event(enable_timing=True)
@@ -459,17 +512,23 @@ class _VHFOpt:
                     _ptr(pair_x), _ptr(q_x), len(pair_x),
                     _ptr(rl['pair']), _ptr(rl['q']), _ptr(rl['rec']),
                     _ptr(rl['row_ptr']), _ptr(rl['row_p']), _ptr(rl['row_qmax']), rl['nrows'],
-                    _ptr(dm_cond), cutoff, dm_penalty, dedupe, rank, world, head, stream, float(omega))
+                    _ptr(dm_cond), cutoff, dm_penalty, dedupe, l_rank, l_world, head, stream, float(omega))
             else:
                 pair_y, q_y = self.bas_pair_cache[ky][:2]
                 rec_y = self.bas_pair_cache[ky][3]
                 err = lib.B200_build_jk_class(
                     _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
                     _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
-                    _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, rank, world, head, stream,
+                    _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, l_rank, l_world, head, stream,
                     _ptr(rec_y), float(omega))
             if err:
                 raise RuntimeError('J/K launch failed for class %s (%s)' % (tuple(lprim), mode))
+            if measuring:
+                if dev.type == 'cuda':
+                    tm1.record()
+                    timers.append((it, tm0, tm1))
+                else:
+                    timers.append((it, tm0, time.perf_counter()))
             if self.class_timing is not None and dev.type == 'cuda':
                 ev1.record()
                 ev1.synchronize()
@@ -489,8 +548,18 @@ class _VHFOpt:
                 ev.record(st)
                 main.wait_event(ev)
 
+        if measuring:
+            cost = np.zeros(len(tasks))
+            if dev.type == 'cuda':
+                torch.cuda.current_stream().synchronize()
+            for it, a, b in timers:
+                cost[it] = a.elapsed_time(b) if dev.type == 'cuda' else (b - a) * 1e3
+            flat[nmat * nao * nao:] = torch.as_tensor(cost, device=dev)
         if world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(out)       # one collective per build over [vj|vk|vkT]
+            torch.distributed.all_reduce(flat)      # one collective per build over [vj|vk|vkT] (+ launch times)
+        if measuring:
+            # summed over ranks = GPU time of the whole launch; identical on every rank after the reduce
+            self._launch_cost = flat[nmat * nao * nao:].cpu().numpy().copy()
 
         # symmetrisation of the partial sums (reference: jk.py:594-616)
         if with_k:

@@ -348,3 +348,124 @@ def test_rys_build_k_reference_signature():
     vk = vk + vk.transpose(1, 2)
     ref = opt.get_k(dms, 1, omega=omega, lr_factor=lr, sr_factor=sr)
     assert abs(vk - ref).max() < 1e-10
+
+
+def test_rys_build_j_reference_name_vs_oracle():
+    """RYS_build_j / RYS_init_rysj_constant (reference: rys_contract_j.cu:824-956, jk.py:681-746) driven by
+    the reference's per-group loop; the result (after the reference's post-processing 2*(J + J^T)) is
+    compared with the CPU ORACLE's J, not with another GPU path."""
+    import ctypes
+    import math
+    from gpu4pyscf_b200.scf import jk
+    from gpu4pyscf_b200.lib import loader
+    oracle = _oracle()
+    lib = loader.load_library()
+    mol = molecules.water('def2-tzvp')
+    np.random.seed(3)
+    nao = mol.nao
+    dm = np.random.rand(nao, nao)
+    dm = dm + dm.T
+    opt = jk._VHFOpt(mol).build()
+    smol = opt.sorted_mol
+    dms = opt.apply_coeff_C_mat_CT(torch.as_tensor(dm, device=opt.device)[None]).contiguous()
+    nbas, naos = smol.nbas, smol.nao
+    dm_cond = torch.empty((nbas, nbas), dtype=torch.float32, device=opt.device)
+    lib.B200_condense(jk._ptr(dm_cond), jk._ptr(dms), 1, naos, jk._ptr(opt.rys_envs._keep[3]), nbas, None)
+    offs = np.append(0, np.cumsum(smol.l_ctr_counts))
+    ng = len(smol.l_ctr_counts)
+    bas_host = np.ascontiguousarray(smol._bas, dtype=np.int32)
+    env_host = np.ascontiguousarray(smol._env, dtype=np.float64)
+    pool = torch.zeros(16, dtype=torch.int32, device=opt.device)
+    vj = torch.zeros_like(dms)
+    dmax = float(dm_cond.max())
+    assert lib.RYS_init_rysj_constant() == 0
+    torch.cuda.synchronize()
+    for i in range(ng):
+        for j in range(i + 1):
+            for k in range(i + 1):
+                for l in range(k + 1):
+                    pij, qij = opt.bas_pair_cache[i, j][:2]
+                    pkl, qkl = opt.bas_pair_cache[k, l][:2]
+                    shls = (ctypes.c_int * 8)(offs[i], offs[i + 1], offs[j], offs[j + 1],
+                                              offs[k], offs[k + 1], offs[l], offs[l + 1])
+                    err = lib.RYS_build_j(
+                        jk._ptr(vj), jk._ptr(dms), 1, naos, ctypes.byref(opt.rys_envs), None, shls,
+                        len(pij), len(pkl), jk._ptr(pij), jk._ptr(pkl), jk._ptr(qij), jk._ptr(qkl),
+                        jk._ptr(qij), jk._ptr(qkl), None, jk._ptr(dm_cond), math.log(1e-13), dmax, jk._ptr(pool),
+                        bas_host.ctypes.data_as(ctypes.c_void_p), env_host.ctypes.data_as(ctypes.c_void_p))
+                    assert err == 0
+    torch.cuda.synchronize()
+    vj = 2. * vj
+    vj = opt.apply_coeff_CT_mat_C(vj + vj.transpose(1, 2))[0].cpu().numpy()
+    rj = oracle.get_jk(mol, dm, hermi=1)[0]
+    assert abs(vj - rj).max() < 1e-10
+    # get_j (the public J-only entry) against the oracle as well
+    vj2 = jk.get_j(mol, dm, hermi=1).cpu().numpy()
+    assert abs(vj2 - rj).max() < 1e-10
+
+
+def test_int2e_qcond_estimator_reference_signature():
+    """int2e_qcond_estimator with the reference's argument list (nr_sr_estimator.cu:416-430) for the full-range,
+    long-range and short-range operators, against the oracle's sqrt(max|(ij|ij)|) (reference tolerance:
+    1e-3 log units, test_scf_jk.py:328-356; here 2e-5, float32 storage)."""
+    import ctypes
+    from gpu4pyscf_b200.scf import jk
+    from gpu4pyscf_b200.lib import loader
+    oracle = _oracle()
+    lib = loader.load_library()
+    mol = molecules.mol1_lmax(4)
+    opt = jk._VHFOpt(mol).build()
+    smol = opt.sorted_mol
+    nbas = smol.nbas
+    vals = list(opt.bas_pair_cache.values())
+    ids = torch.cat([v[0] for v in vals]).contiguous()
+    o = np.append(0, np.cumsum([len(v[0]) for v in vals]))
+    spo = np.hstack([np.arange(o[g], o[g + 1], 5) for g in range(len(vals))] + [[o[-1]]]).astype(np.int32)
+    spo = torch.as_tensor(spo, device=opt.device)
+    idn = ids.cpu().numpy().astype(np.int64)
+    for om, lrf, srf in ((0., 1., 1.), (0.4, 1., 0.), (-0.4, 0., 1.)):
+        q = torch.empty(len(ids), dtype=torch.float32, device=opt.device)
+        torch.cuda.synchronize()
+        assert lib.int2e_qcond_estimator(jk._ptr(q), ctypes.byref(opt.rys_envs), 0, len(spo) - 1, jk._ptr(ids),
+                                         jk._ptr(spo), None, om, lrf, srf) == 0
+        torch.cuda.synchronize()
+        ref = np.log(oracle.q_cond(smol, omega=om)[idn // nbas, idn % nbas])
+        assert abs(q.cpu().numpy() - ref).max() < 2e-5, (om, abs(q.cpu().numpy() - ref).max())
+
+
+def test_pair_prescreen_is_conservative():
+    """B200_pair_prescreen (overlap estimate, reference overlap.cu:2163-2223) on a 40-atom Taxol fragment:
+    every pair it drops has a Schwarz bound that could not survive against the largest bound of the
+    molecule at direct_scf_tol = 1e-13, i.e. the prescreen only removes what the q filter removes anyway."""
+    import ctypes
+    import math
+    from gpu4pyscf_b200.scf import jk
+    from gpu4pyscf_b200.lib import loader
+    lib = loader.load_library()
+    mol = _taxol(40)
+    opt = jk._VHFOpt(mol).build()
+    smol = opt.sorted_mol
+    nbas = smol.nbas
+    kept = torch.cat([v[0] for v in opt.bas_pair_cache.values()]).to(torch.int64)
+    qmax = max(float(v[1].max()) for v in opt.bas_pair_cache.values() if len(v[1]))
+    mask = torch.ones(nbas * nbas, dtype=torch.bool, device=opt.device)
+    mask[kept] = False
+    ii, jj = torch.meshgrid(torch.arange(nbas, device=opt.device), torch.arange(nbas, device=opt.device), indexing='ij')
+    dropped = torch.nonzero(mask & (ii >= jj).reshape(-1)).reshape(-1)
+    assert len(dropped) > 1000 and len(kept) > 1000
+    offs = np.append(0, np.cumsum(smol.l_ctr_counts))
+    grp = torch.as_tensor(np.repeat(np.arange(len(smol.l_ctr_counts)), smol.l_ctr_counts), device=opt.device)
+    uniq = smol.uniq_l_ctr
+    worst = -1e30
+    for gi in range(len(offs) - 1):
+        for gj in range(gi + 1):
+            sel = dropped[(grp[dropped // nbas] == gi) & (grp[dropped % nbas] == gj)]
+            if len(sel) == 0:
+                continue
+            ids = sel.to(torch.int32).contiguous()
+            q = torch.empty(len(ids), dtype=torch.float32, device=opt.device)
+            assert lib.B200_qcond(jk._ptr(q), ctypes.byref(opt.rys_envs), jk._ptr(ids), len(ids),
+                                  int(uniq[gi, 0]), int(uniq[gj, 0]), int(uniq[gi, 1]), int(uniq[gj, 1]),
+                                  loader.current_stream_ptr()) == 0
+            worst = max(worst, float(q.max()))
+    assert worst + qmax < math.log(1e-13), (worst, qmax)

@@ -29,7 +29,21 @@ nao = mol.nao
 dm = np.random.rand(nao, nao)
 dm = dm + dm.T
 opt = jk._VHFOpt(mol).build()
-vj, vk = jk.get_jk(mol, dm, hermi=1, vhfopt=opt)          # partitioned over 2 ranks + all_reduce
+# first build: work items of every launch dealt over the 2 ranks, launch times measured and reduced with [J|K]
+vj0, vk0 = jk.get_jk(mol, dm, hermi=1, vhfopt=opt)
+assert opt._launch_cost is not None and len(opt._launch_cost) == len(opt.class_tasks())
+owners = jk._lpt_owners(opt._launch_cost, 2)
+assert set(owners) == {0, 1}                               # both ranks own launches
+# second build: light launches whole on one rank (longest first), heavy ones item-dealt; same single all_reduce
+os.environ['B200_SPLIT_MIN_MS'] = str(float(np.median(opt._launch_cost)))
+owners = jk._lpt_owners(opt._launch_cost, 2, float(os.environ['B200_SPLIT_MIN_MS']))
+assert -1 in owners and 0 in owners and 1 in owners
+vj, vk = jk.get_jk(mol, dm, hermi=1, vhfopt=opt)
+assert abs(vj - vj0).max() < 1e-11 and abs(vk - vk0).max() < 1e-11
+# every launch whole on one rank
+os.environ['B200_PARTITION'] = 'cost'
+vj, vk = jk.get_jk(mol, dm, hermi=1, vhfopt=opt)
+assert abs(vj - vj0).max() < 1e-11 and abs(vk - vk0).max() < 1e-11
 opt1 = jk._VHFOpt(mol).build()
 opt1.rank, opt1.world = 0, 1                               # same build on one rank, no collective
 vj1, vk1 = jk.get_jk(mol, dm, hermi=1, vhfopt=opt1)
