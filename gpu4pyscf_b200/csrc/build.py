@@ -31,7 +31,7 @@ def _generate(variant=None, genenv=None):
 
 
 # headers only capi.cu includes: a change there does not rebuild the class instantiation units
-CAPI_ONLY = ('qcond.cuh', 'rys_tables.h')
+CAPI_ONLY = ('qcond.cuh', 'rys_tables.h', 'ao_transform.cuh')
 
 
 def _newest_header(capi=True):

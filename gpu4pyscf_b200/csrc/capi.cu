@@ -5,6 +5,7 @@
 #include "rt.h"
 #include "jk_launch.cuh"
 #include "qcond.cuh"
+#include "ao_transform.cuh"
 #include "rys_tables.h"
 #include "jk_dispatch.inc"
 
@@ -507,6 +508,44 @@ int B200_pair_records(double *out, const RysIntEnvVars *envs, const uint32_t *pa
             (const int *)envs->bas, (const double *)envs->env, (const int *)envs->ao_loc, envs->nbas,
             nprim_i, nprim_j);
     return rt_last_error("pair_record_kernel");
+}
+
+// out (n, nrow, nrow) = A in A^T for a CSR matrix A (nrow x ncol_in) and n square inputs (ncol_in x ncol_in);
+// tmp: scratch of n * nrow * ncol_in doubles.  With A = C: D_sorted = C D C^T (apply_C_mat_CT); with
+// A = C^T: V = C^T V_sorted C (apply_CT_mat_C).  Replaces the reference's bra_/ket_ transform entries
+// (mole_helper.cu:1735-1908).
+int B200_sparse_A_mat_AT(double *out, double *tmp, const double *in, int n, int nrow, int ncol_in,
+                         const int *row_ptr, const int *col, const double *val, void *stream)
+{
+    if (n <= 0 || nrow <= 0 || ncol_in <= 0) return 0;
+#ifdef CPU_EMUL
+    // the emulator runs 1-D grids: plain loops, same arithmetic order
+    (void)stream;
+    for (int m = 0; m < n; ++m)
+        for (int r = 0; r < nrow; ++r)
+            for (int c = 0; c < ncol_in; ++c) {
+                double s = 0.;
+                for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k)
+                    s += val[k] * in[((size_t)m * ncol_in + col[k]) * ncol_in + c];
+                tmp[((size_t)m * nrow + r) * ncol_in + c] = s;
+            }
+    for (int m = 0; m < n; ++m)
+        for (int r = 0; r < nrow; ++r)
+            for (int j = 0; j < nrow; ++j) {
+                double s = 0.;
+                for (int k = row_ptr[j]; k < row_ptr[j + 1]; ++k)
+                    s += val[k] * tmp[((size_t)m * nrow + r) * ncol_in + col[k]];
+                out[((size_t)m * nrow + r) * nrow + j] = s;
+            }
+    return 0;
+#else
+    const int nt = 128;
+    spmm_left_kernel<<<dim3((ncol_in + nt - 1) / nt, nrow, n), nt, 0, (cudaStream_t)stream>>>(
+        tmp, in, row_ptr, col, val, nrow, ncol_in, ncol_in);
+    spmm_right_kernel<<<dim3((nrow + nt - 1) / nt, nrow, n), nt, 0, (cudaStream_t)stream>>>(
+        out, tmp, row_ptr, col, val, nrow, nrow, ncol_in);
+    return rt_last_error("sparse AO transform");
+#endif
 }
 
 int B200_condense(float *out, const double *dm, int n_dm, int nao, const int *ao_loc, int nbas,

@@ -417,15 +417,50 @@ class SortedGTO:
             self._dev_cache[key] = torch.as_tensor(self.ctr_coeff, device=device)
         return self._dev_cache[key]
 
+    def _csr_on(self, device, transpose):
+        '''CSR form (row_ptr, col, val) of C (transpose=False) or C^T on `device`'''
+        import torch
+        key = (str(device), 'csrT' if transpose else 'csr')
+        if key not in self._dev_cache:
+            A = self.ctr_coeff.T if transpose else self.ctr_coeff
+            rows, cols = np.nonzero(A)
+            row_ptr = np.zeros(A.shape[0] + 1, dtype=np.int32)
+            np.cumsum(np.bincount(rows, minlength=A.shape[0]), out=row_ptr[1:])
+            self._dev_cache[key] = (torch.as_tensor(row_ptr, device=device),
+                                    torch.as_tensor(cols.astype(np.int32), device=device),
+                                    torch.as_tensor(np.ascontiguousarray(A[rows, cols]), device=device))
+        return self._dev_cache[key]
+
+    def _sparse_A_mat_AT(self, mat, transpose):
+        import ctypes
+        import torch
+        from ..lib import loader
+        lib = loader.load_library()
+        shape = mat.shape
+        ncol = shape[-1]
+        mats = mat.reshape(-1, ncol, ncol).contiguous()
+        nrow = self.ctr_coeff.shape[1] if transpose else self.ctr_coeff.shape[0]
+        row_ptr, col, val = self._csr_on(mat.device, transpose)
+        n = mats.shape[0]
+        out = torch.empty((n, nrow, nrow), dtype=torch.float64, device=mat.device)
+        tmp = torch.empty((n, nrow, ncol), dtype=torch.float64, device=mat.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        if lib.B200_sparse_A_mat_AT(p(out), p(tmp), p(mats), n, nrow, ncol, p(row_ptr), p(col), p(val),
+                                    loader.current_stream_ptr()):
+            raise RuntimeError('B200_sparse_A_mat_AT failed')
+        return out.reshape(shape[:-2] + (nrow, nrow))
+
     def apply_C_mat_CT(self, mat):
-        '''C . mat . C^T : original (sph/contracted) -> sorted Cartesian'''
-        C = self._coeff_on(mat.device)
-        return C @ mat @ C.T
+        '''C . mat . C^T : original (sph/contracted) -> sorted Cartesian, through the sparse transform
+        kernels (reference: SortedGTO.apply_C_mat_CT, gto/mole.py:906-921, bra_/ket_ kernels of
+        mole_helper.cu:1735-1908)'''
+        assert mat.shape[-1] == self.ctr_coeff.shape[1] and mat.dtype.is_floating_point
+        return self._sparse_A_mat_AT(mat, False)
 
     def apply_CT_mat_C(self, mat):
-        '''C^T . mat . C : sorted Cartesian -> original'''
-        C = self._coeff_on(mat.device)
-        return C.T @ mat @ C
+        '''C^T . mat . C : sorted Cartesian -> original (reference: gto/mole.py:923-938)'''
+        assert mat.shape[-1] == self.ctr_coeff.shape[0]
+        return self._sparse_A_mat_AT(mat, True)
 
     def apply_C_dot(self, mat):
         C = self._coeff_on(mat.device)

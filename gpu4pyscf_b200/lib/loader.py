@@ -87,6 +87,8 @@ def load_library(name='libgvhf_rys_b200'):
         vp, vp, c_int, c_int, vp, vp, vp, c_int, c_int,
         vp, vp, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp, vp]
     lib.RYS_init_rysj_constant.restype = c_int
+    lib.B200_sparse_A_mat_AT.restype = c_int
+    lib.B200_sparse_A_mat_AT.argtypes = [vp, vp, vp, c_int, c_int, c_int, vp, vp, vp, vp]
     lib.B200_set_counter.restype = c_int
     lib.B200_set_counter.argtypes = [vp]
     lib.B200_condense.restype = c_int

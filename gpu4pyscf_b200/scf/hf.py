@@ -1,0 +1,222 @@
+"""The callers that sit directly on the J/K path, with the reference's method names and argument
+meaning: ``SCF.get_jk / get_j / get_k`` (gpu4pyscf/scf/hf.py:933-972), ``RHF.get_veff`` with the
+incremental ``dm_last / vhf_last`` build (hf.py:91-109), ``UHF.get_veff`` (uhf.py:386-406) and a plain
+DIIS ``kernel`` loop in the shape of hf.py:206-342.
+
+Scope: the product of this repository is the J/K build; the reference's SCF drivers stay the
+reference's.  These classes exist so that the plugin is exercised the way ``mf.get_jk`` / ``get_veff``
+exercise it (one ``_VHFOpt`` per omega cached on the mean-field object, separate J and K passes,
+incremental Fock builds) and so that the SCF-energy parity of the north star can be asserted.  The
+one-electron part is NOT in scope: ``kernel`` takes the core Hamiltonian and overlap from the caller
+(``mf.hcore``, ``mf.ovlp``: in gpu4pyscf they come from libcint on the host, in the tests from the CPU
+oracle).  Everything stays on the device (torch tensors); there is no CPU fallback."""
+import numpy as np
+import torch
+
+from . import jk
+
+__all__ = ['SCF', 'RHF', 'UHF']
+
+
+class SCF:
+    direct_scf = True
+    direct_scf_tol = 1e-13
+    conv_tol = 1e-10
+    max_cycle = 80
+    diis_space = 8
+
+    def __init__(self, mol):
+        self.mol = mol
+        self._opt_gpu = {}            # omega -> _VHFOpt, as hf.py:936-944
+        self.hcore = None             # (nao, nao) core Hamiltonian, set by the caller
+        self.ovlp = None              # (nao, nao) overlap, set by the caller
+        self.e_nuc = None
+        self.mo_energy = self.mo_coeff = self.mo_occ = None
+        self.e_tot = None
+        self.converged = False
+        self.cycles = 0
+
+    # ---- the hot path --------------------------------------------------
+    def _vhfopt(self, omega):
+        opt = self._opt_gpu.get(omega)
+        if opt is None:
+            with self.mol.with_range_coulomb(omega):
+                opt = self._opt_gpu[omega] = jk._VHFOpt(self.mol, self.direct_scf_tol).build()
+        return opt
+
+    def get_jk(self, mol=None, dm=None, hermi=1, with_j=True, with_k=True,
+               omega=None, lr_factor=None, sr_factor=None):
+        mol = self.mol if mol is None else mol
+        if dm is None:
+            dm = self.make_rdm1()
+        if omega is None:
+            omega = mol.omega
+        return jk.get_jk(mol, dm, hermi, self._vhfopt(omega), with_j, with_k, omega, lr_factor, sr_factor)
+
+    def get_j(self, mol=None, dm=None, hermi=1, omega=None):
+        mol = self.mol if mol is None else mol
+        if omega is None:
+            omega = mol.omega
+        with mol.with_range_coulomb(omega):
+            return jk.get_j(mol, dm, hermi, self._vhfopt(omega))
+
+    def get_k(self, mol=None, dm=None, hermi=1, omega=None, lr_factor=None, sr_factor=None):
+        mol = self.mol if mol is None else mol
+        if omega is None:
+            omega = mol.omega
+        with mol.with_range_coulomb(omega):
+            return jk.get_k(mol, dm, hermi, self._vhfopt(omega), omega, lr_factor, sr_factor)
+
+    # ---- the loop around it ---------------------------------------------
+    def _dev(self, a):
+        opt = self._vhfopt(self.mol.omega)
+        return jk._as_device_tensor(a, opt.device)
+
+    def _orthogonaliser(self, s):
+        se, sv = torch.linalg.eigh(s)
+        return sv / se.sqrt()
+
+    def kernel(self, dm0=None):
+        '''DIIS SCF on top of get_veff; hcore, ovlp (and e_nuc) must have been set.'''
+        assert self.hcore is not None and self.ovlp is not None, 'set mf.hcore and mf.ovlp (one-electron integrals)'
+        h = self._dev(self.hcore)
+        s = self._dev(self.ovlp)
+        x = self._orthogonaliser(s)
+        enuc = float(self.mol.energy_nuc() if self.e_nuc is None else self.e_nuc)
+        dm = self._dev(dm0) if dm0 is not None else self._core_guess(h, x)
+        vhf = self.get_veff(self.mol, dm)
+        fs, es = [], []
+        e_last = None
+        self.converged = False
+        for it in range(self.max_cycle):
+            f = self._fock(h, vhf)
+            e_tot = self.energy_elec(dm, h, vhf) + enuc
+            err = self._diis_error(f, dm, s, x)
+            fs.append(f)
+            es.append(err)
+            fs, es = fs[-self.diis_space:], es[-self.diis_space:]
+            if len(fs) > 1:
+                n = len(fs)
+                b = torch.zeros((n + 1, n + 1), dtype=torch.float64, device=h.device)
+                b[-1, :n] = 1.
+                b[:n, -1] = 1.
+                for i in range(n):
+                    for j in range(i + 1):
+                        b[i, j] = b[j, i] = (es[i] * es[j]).sum()
+                rhs = torch.zeros(n + 1, dtype=torch.float64, device=h.device)
+                rhs[-1] = 1.
+                try:
+                    coef = torch.linalg.solve(b, rhs)[:n]
+                    f = sum(c * fi for c, fi in zip(coef, fs))
+                except RuntimeError:
+                    pass
+            self.cycles = it + 1
+            if e_last is not None and abs(e_tot - e_last) < self.conv_tol and float(err.abs().max()) < 1e-6:
+                self.converged = True
+                self.e_tot = e_tot
+                self._dm = dm
+                return e_tot
+            e_last = e_tot
+            dm_last, vhf_last = dm, vhf
+            dm = self._new_density(f, x)
+            # incremental Fock build: J/K of the density CHANGE, as the reference does (hf.py:94-99)
+            vhf = self.get_veff(self.mol, dm, dm_last, vhf_last)
+        self.e_tot = e_tot
+        self._dm = dm
+        return e_tot
+
+    def make_rdm1(self):
+        return self._dm
+
+
+class RHF(SCF):
+    def get_veff(self, mol=None, dm=None, dm_last=None, vhf_last=None, hermi=1):
+        '''J - K/2 with separate J and K passes (reference: hf.py:91-109)'''
+        mol = self.mol if mol is None else mol
+        ddm = self._dev(dm)
+        if dm_last is not None and self.direct_scf:
+            assert vhf_last is not None
+            ddm = ddm - self._dev(dm_last)
+        else:
+            vhf_last = None
+        vj = self.get_j(mol, ddm, hermi)
+        vhf = self.get_k(mol, ddm, hermi)
+        vhf = vj - .5 * vhf
+        if vhf_last is not None:
+            vhf = vhf + vhf_last
+        return vhf
+
+    def _nocc(self):
+        return (self.mol.nelectron) // 2
+
+    def _fock(self, h, vhf):
+        return h + vhf
+
+    def energy_elec(self, dm, h, vhf):
+        return float((dm * (h + .5 * vhf)).sum())
+
+    def _diis_error(self, f, dm, s, x):
+        return x.T @ (f @ dm @ s - s @ dm @ f) @ x
+
+    def _new_density(self, f, x):
+        e, c = torch.linalg.eigh(x.T @ f @ x)
+        c = x @ c
+        self.mo_energy, self.mo_coeff = e, c
+        nocc = self._nocc()
+        occ = torch.zeros_like(e)
+        occ[:nocc] = 2.
+        self.mo_occ = occ
+        return 2. * c[:, :nocc] @ c[:, :nocc].T
+
+    def _core_guess(self, h, x):
+        return self._new_density(h, x)
+
+
+class UHF(SCF):
+    def get_veff(self, mol=None, dm=None, dm_last=None, vhf_last=None, hermi=1):
+        '''(J[Da+Db] - K[Da], J[Da+Db] - K[Db]): one J pass, one K pass over both spin densities
+        (reference: uhf.py:386-406)'''
+        mol = self.mol if mol is None else mol
+        dm = self._dev(dm)
+        if dm.ndim == 2:
+            dm = torch.stack([dm * .5, dm * .5])
+        ddm = dm
+        if dm_last is not None and self.direct_scf:
+            assert vhf_last is not None
+            ddm = dm - self._dev(dm_last)
+        else:
+            vhf_last = None
+        vj = self.get_j(mol, ddm[0] + ddm[1], hermi)
+        vhf = vj[None] - self.get_k(mol, ddm, hermi)
+        if vhf_last is not None:
+            vhf = vhf + vhf_last
+        return vhf
+
+    def _nocc(self):
+        na, nb = self.mol.nelec
+        return na, nb
+
+    def _fock(self, h, vhf):
+        return h[None] + vhf
+
+    def energy_elec(self, dm, h, vhf):
+        return float((dm * (h[None] + .5 * vhf)).sum())
+
+    def _diis_error(self, f, dm, s, x):
+        return torch.stack([x.T @ (f[k] @ dm[k] @ s - s @ dm[k] @ f[k]) @ x for k in range(2)])
+
+    def _new_density(self, f, x):
+        if f.ndim == 2:
+            f = torch.stack([f, f])
+        dms, es, cs = [], [], []
+        for k, n in enumerate(self._nocc()):
+            e, c = torch.linalg.eigh(x.T @ f[k] @ x)
+            c = x @ c
+            es.append(e)
+            cs.append(c)
+            dms.append(c[:, :n] @ c[:, :n].T)
+        self.mo_energy, self.mo_coeff = torch.stack(es), torch.stack(cs)
+        return torch.stack(dms)
+
+    def _core_guess(self, h, x):
+        return self._new_density(h, x)

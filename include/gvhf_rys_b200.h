@@ -193,6 +193,14 @@ int RYS_build_j(double *vj, double *dm, int n_dm, int nao,
                 uint32_t *pool, int *bas, double *env);
 int RYS_init_rysj_constant(void);
 
+/* Sparse AO transform  out (n, nrow, nrow) = A in A^T  for a CSR matrix A (nrow x ncol_in; row_ptr[nrow+1],
+ * col, val) and n square inputs (ncol_in x ncol_in); tmp = scratch of n*nrow*ncol_in doubles.  A = C gives
+ * D_sorted = C D C^T, A = C^T gives V = C^T V_sorted C, where C (nao_sorted x nao) is the recontraction x
+ * cart->sph map of the sorted basis.  Replaces the bra_/ket_ {sph,cart}2sorted / sorted2{sph,cart} entries
+ * of lib/gvhf-rys/mole_helper.cu:1735-1908 (gto/mole.py:790-938) with one entry on a CSR data model. */
+int B200_sparse_A_mat_AT(double *out, double *tmp, const double *in, int n, int nrow, int ncol_in,
+                         const int *row_ptr, const int *col, const double *val, void *stream);
+
 /* dm_cond[i*nbas+j] = log(max |D_n[a,b]| + 1e-300) over the AO block of shell
  * pair (i,j) and all n_dm matrices.  Replaces the CuPy RawKernel behind
  * condense('absmax', ...) (gpu4pyscf/lib/cupy_helper.py:1068-1184, used at
