@@ -39,7 +39,7 @@ METRIC = 'J/K build s/iter (direct SCF, Taxol def2-TZVP)'
 # F_alg of one full build (SURVEY.md 8d flop model x quartets counted by the GPU
 # kernels for the bench density; profiles/bench_r1_baseline.json).  Only used to
 # scale the CPU arm's bounded sample to the full workload.
-F_ALG_FULL = {('113_Taxol', 'def2-tzvp'): 4.9499377e13}
+F_ALG_FULL = {('113_Taxol', 'def2-tzvp'): 4.8760375e13}
 MOLDIR = os.path.join(ROOT, 'gpu4pyscf_b200', 'data', 'molecules')
 
 
@@ -141,6 +141,46 @@ def committed_counters(mol_name, basis):
         return None
     with open(path) as f:
         return json.load(f)
+
+
+def measured_cpu_runs(dev=None):
+    """Full-molecule CPU-oracle runs that were actually measured (not extrapolated): the golden fixtures
+    under tests/golden record the oracle's wall time (8 cores of the build container, no screening).
+    With a device, the same J/K build is timed on the GPU next to it."""
+    import glob
+    import numpy as np
+    out = []
+    for path in sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'jk_*.npz'))):
+        g = np.load(path)
+        parts = os.path.basename(path)[3:-4].split('_')
+        natoms = int(parts.pop()) if parts[-1].isdigit() and not parts[-2].isdigit() else None
+        basis = parts.pop()
+        name = '_'.join(parts)
+        row = {'mol': name, 'basis': basis, 'natoms': natoms, 'nao': int(g['nao']),
+               'cpu_oracle_seconds': float(g['oracle_seconds']), 'cpu_cores': 8,
+               'cpu_note': 'oracle/md_jk.c, OpenMP, no screening, build container (tests/golden/make_golden_jk.py)'}
+        if dev is not None:
+            try:
+                import torch
+                from gpu4pyscf_b200.scf import jk
+                mol = load_mol(name, basis, natoms)
+                dm = torch.as_tensor(decaying_density(mol), device=dev)
+                opt = jk._VHFOpt(mol).build()
+                opt.world, opt.rank = 1, 0
+                for _ in range(2):
+                    jk.get_jk(mol, dm, hermi=1, vhfopt=opt)
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                jk.get_jk(mol, dm, hermi=1, vhfopt=opt)
+                e1.record()
+                e1.synchronize()
+                row['gpu_seconds'] = e0.elapsed_time(e1) * 1e-3
+            except Exception as e:          # a missing basis must not kill the bench line
+                row['gpu_error'] = str(e)[:200]
+        out.append(row)
+    return out
 
 
 # ----------------------------------------------------------------------
@@ -351,7 +391,8 @@ def main():
                              'first %d atoms of %s/%s (nao %d, %d quartets, F_alg %.3e) took %.2f s; value = that time x '
                              'F_alg(full)/F_alg(sample) = x %.1f' % (args.cpu_atoms, args.mol, args.basis, nao_c, n, f_c, t,
                                                                      f_alg_total / f_c),
-                   'sample_seconds': t, 'sample_gflops': f_c / t / 1e9}
+                   'sample_seconds': t, 'sample_gflops': f_c / t / 1e9,
+                   'measured_full_molecule_runs': measured_cpu_runs(dev)}
         nbytes = nao * nao * 8
         # F_hw and DRAM traffic come from a committed ncu capture of the same workload (per build, all launches)
         ctr = committed_counters(args.mol, args.basis) if world == 1 else None

@@ -19,8 +19,10 @@ __host__ __device__ constexpr int jkt_minblocks(int nf_total)
 #ifdef JKT_MINBLOCKS_FIXED
     return JKT_MINBLOCKS_FIXED;
 #endif
-    // measured on Taxol (profiles/): 170 registers (3 blocks) beat 96/128 for everything but the (ss|..) classes
-    return nf_total <= 6 ? 5 : (nf_total <= 70 ? 3 : 2);
+    // measured on Taxol (profiles/): 170 registers (3 blocks) beat 96/128 for everything but the (ss|..) classes;
+    // from ~50 live doubles on, 255 registers (2 blocks) win: (20|30) with 70 spills 728 B per thread at 170
+    // registers and stalls 71 % of the time on local-memory loads (profiles/ncu_r2/raw_r2j_20301111_metrics.txt)
+    return nf_total <= 6 ? 5 : (nf_total <= 48 ? 3 : 2);
 }
 
 // block-wide sum of per-thread values through shuffles + one smem stage
