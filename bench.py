@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = 'J/K build s/iter (direct SCF, Taxol def2-TZVP)'
+METRIC = 'J/K build s/iter (direct SCF, Taxol def2-TZVP)'      # other --mol/--basis: named in config.workload
 # F_alg of one full build (SURVEY.md 8d flop model x quartets counted by the GPU
 # kernels for the bench density; profiles/bench_r1_baseline.json).  Only used to
 # scale the CPU arm's bounded sample to the full workload.
@@ -120,6 +120,12 @@ def physical_gpu_index(local):
         except Exception:
             return local
     return local
+
+
+def metric_name(args):
+    if (args.mol, args.basis.lower()) == ('113_Taxol', 'def2-tzvp'):
+        return METRIC
+    return 'J/K build s/iter (direct SCF, %s %s)' % (args.mol, args.basis)
 
 
 def workload_config(mol_name, basis, world, extra=None):
@@ -267,7 +273,7 @@ def run_reference(args, rank):
               % (args.cpu_atoms, args.mol, args.basis, nao, n, f_c, t, scale))
     v = t * scale
     out = {
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 's', 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': metric_name(args), 'value': v, 'unit': 's', 'n_gpus': args.gpus,
         'steps': len(times), 'warmup': 1, 'ms_per_step': v * 1e3, 'higher_is_better': False,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args.mol, args.basis, args.gpus),
@@ -323,6 +329,8 @@ def main():
     dmt = dm_pinned.to(dev)
     dms = opt.apply_coeff_C_mat_CT(dmt.reshape(1, nao, nao)).contiguous()
 
+    rank_ms = {}      # per-rank device time of the timed region (ms per step), N > 1
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -341,6 +349,9 @@ def main():
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            rank_ms[fn.__name__] = [float(x) / steps for x in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -401,7 +412,7 @@ def main():
         achieved = f_eff / (ms_step * 1e-3) / 1e12
         nominal = 148 * 64 * 2 * 1.965e9 / 1e12                 # 148 SMs x 64 DFMA lanes x 2 flop x 1.965 GHz
         out = {
-            'metric': METRIC, 'value': ms_step * 1e-3, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
+            'metric': metric_name(args), 'value': ms_step * 1e-3, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': False,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(args.mol, args.basis, world, {
@@ -433,6 +444,8 @@ def main():
                                        'tflops': top[1][2] / (top[1][0] * 1e-3) / 1e12 if top[1][0] else None}},
             'cpu_baseline': cpu,
             'e2e': {'value': ms_e2e * 1e-3, 'unit': 's', 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': 2 * nbytes},
+            'rank_ms_per_step': ({'max': max(rank_ms['step_resident']), 'min': min(rank_ms['step_resident']),
+                                  'mean': sum(rank_ms['step_resident']) / world} if rank_ms.get('step_resident') else None),
             'gpu_launches': (nlaunch + 1) * args.steps,   # class kernels + condense per build
             'clocks': clocks,
         }

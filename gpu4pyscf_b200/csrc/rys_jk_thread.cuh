@@ -25,6 +25,27 @@ __host__ __device__ constexpr int jkt_minblocks(int nf_total)
     return nf_total <= 6 ? 5 : (nf_total <= 48 ? 3 : 2);
 }
 
+// A class whose integral block does not fit the register file CAN be evaluated in NPART passes over
+// the Cartesian components c of shell r (NCP = NFR / NPART components per pass): roots and recurrences
+// are recomputed per pass, the live integral block shrinks NPART times and the spills go away
+// ((20|30): 264 -> 24 B of stack).  Measured on Taxol with JKT_PART_MIN = 48 (profiles/launch_table_r2l_threadsplit.txt):
+// uncontracted launches gain 3-8 % ((20|30) 73 -> 69 ms, (11|30) 41 -> 38 ms), contracted launches lose up to
+// 2x because the recurrences are redone per primitive quartet and pass ((11|11) p-contracted 29 -> 46 ms);
+// +109 ms per build in total, so the split is compiled out by default.
+#ifndef JKT_PART_MAX
+#define JKT_PART_MAX 50          // integrals per pass
+#endif
+#ifndef JKT_PART_MIN
+#define JKT_PART_MIN 1000000     // classes up to this many live doubles are not split (default: never split)
+#endif
+__host__ __device__ constexpr int jkt_nparts(int nfpq, int nfr, int nfs, int ndm)
+{
+    if (nfpq * nfr * nfs + nfr * nfs * ndm <= JKT_PART_MIN) return 1;
+    for (int p = 2; p <= nfr; ++p)
+        if (nfr % p == 0 && nfpq * (nfr / p) * nfs <= JKT_PART_MAX) return p;
+    return 1;
+}
+
 // block-wide sum of per-thread values through shuffles + one smem stage
 __device__ __forceinline__ double jkt_warp_sum(double v)
 {
@@ -44,16 +65,19 @@ __host__ __device__ inline int jkt_warp_doubles(int nrs, int ndm, int nfrs)
 // product of the (p,q) primitive pair with prefactor cpq, rr = {eta, Qx, Qy, Qz, coef}
 // that of the (r,s) pair; A / C are the centres of p / r, AB = A - B, CD = C - D.
 // Recurrences as in the reference (build_rys_gxyz.cuh:18-123), different data flow.
-template <int LP, int LQ, int LR, int LS>
+template <int LP, int LQ, int LR, int LS, int NCP = ncart(LR)>
 __device__ __forceinline__ void jkt_prim_quartet(
-    double (&gout)[ncart(LP) * ncart(LQ) * ncart(LR) * ncart(LS)],
+    double (&gout)[ncart(LP) * ncart(LQ) * NCP * ncart(LS)],
     const double zeta, const double Px, const double Py, const double Pz, const double cpq,
     const double Ax, const double Ay, const double Az, const double ABx, const double ABy, const double ABz,
     const double *rr, const double Cx, const double Cy, const double Cz,
-    const double CDx, const double CDy, const double CDz, const double omega, const double *rys_tab)
+    const double CDx, const double CDy, const double CDz, const double omega, const double *rys_tab,
+    const int c_lo = 0)
 {
+    // c_lo: first r component of this pass (a constant after unrolling the caller's pass loop);
+    // gout holds the components c_lo .. c_lo + NCP - 1 of shell r
     typedef JKCfg<LP, LQ, LR, LS, 1> C;
-    constexpr int NFP = C::NFP, NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS;
+    constexpr int NFP = C::NFP, NFQ = C::NFQ, NFS = C::NFS;
     constexpr int LPQ = C::LPQ, LRS = C::LRS, NROOTS = C::NROOTS;
     const double eta = rr[0];
     const double PQx = Px - rr[1], PQy = Py - rr[2], PQz = Pz - rr[3];
@@ -151,10 +175,11 @@ __device__ __forceinline__ void jkt_prim_quartet(
 #pragma unroll
         for (int b = 0; b < NFQ; ++b)
 #pragma unroll
-        for (int c = 0; c < NFR; ++c)
+        for (int cc = 0; cc < NCP; ++cc)
 #pragma unroll
         for (int d = 0; d < NFS; ++d) {
-            gout[((a * NFQ + b) * NFR + c) * NFS + d] +=
+            const int c = c_lo + cc;
+            gout[((a * NFQ + b) * NCP + cc) * NFS + d] +=
                 g4[0][((cart_x(LP, a) * (LQ + 1) + cart_x(LQ, b)) * (LR + 1) + cart_x(LR, c)) * (LS + 1) + cart_x(LS, d)]
               * g4[1][((cart_y(LP, a) * (LQ + 1) + cart_y(LQ, b)) * (LR + 1) + cart_y(LR, c)) * (LS + 1) + cart_y(LS, d)]
               * g4[2][((cart_z(LP, a) * (LQ + 1) + cart_z(LQ, b)) * (LR + 1) + cart_z(LR, c)) * (LS + 1) + cart_z(LS, d)];
@@ -164,9 +189,16 @@ __device__ __forceinline__ void jkt_prim_quartet(
 
 template <int LP, int LQ, int LR, int LS, int NDM>
 __global__ void
-__launch_bounds__(JKT_THREADS, jkt_minblocks(ncart(LP) * ncart(LQ) * ncart(LR) * ncart(LS) + ncart(LR) * ncart(LS) * NDM))
+__launch_bounds__(JKT_THREADS,
+                  jkt_minblocks(ncart(LP) * ncart(LQ) * ncart(LR) * ncart(LS)
+                                / jkt_nparts(ncart(LP) * ncart(LQ), ncart(LR), ncart(LS), NDM)
+                                + ncart(LR) * ncart(LS) * NDM
+                                + (jkt_nparts(ncart(LP) * ncart(LQ), ncart(LR), ncart(LS), NDM) > 1
+                                   ? NDM * (ncart(LP) * ncart(LQ) + (ncart(LP) + ncart(LQ)) * ncart(LS)) : 0)))
 rys_jk_thread_kernel(JKTask t)
 {
+    constexpr int NPART = jkt_nparts(ncart(LP) * ncart(LQ), ncart(LR), ncart(LS), NDM);
+    constexpr int NCP = ncart(LR) / NPART;
     typedef JKCfg<LP, LQ, LR, LS, 1> C;
     constexpr int NFP = C::NFP, NFQ = C::NFQ, NFR = C::NFR, NFS = C::NFS;
     constexpr int NFPQ = C::NFPQ, NFRS = C::NFRS;
@@ -348,9 +380,24 @@ rys_jk_thread_kernel(JKTask t)
                 }
                 if (rsh == ssh) fac *= .5;
 
-                double gout[NFPQ * NFRS];
+                // sums that run over all r components: complete after the last pass
+                double jpq[NDM][NFPQ], kps[NDM][NFP][NFS], kqs[NDM][NFQ][NFS];
 #pragma unroll
-                for (int n = 0; n < NFPQ * NFRS; ++n) gout[n] = 0.;
+                for (int idm = 0; idm < NDM; ++idm) {
+#pragma unroll
+                    for (int n = 0; n < NFPQ; ++n) jpq[idm][n] = 0.;
+#pragma unroll
+                    for (int n = 0; n < NFP * NFS; ++n) kps[idm][n / NFS][n % NFS] = 0.;
+#pragma unroll
+                    for (int n = 0; n < NFQ * NFS; ++n) kqs[idm][n / NFS][n % NFS] = 0.;
+                }
+
+#pragma unroll
+                for (int part = 0; part < NPART; ++part) {
+                const int c_lo = part * NCP;
+                double gout[NFPQ * NCP * NFS];
+#pragma unroll
+                for (int n = 0; n < NFPQ * NCP * NFS; ++n) gout[n] = 0.;
 
                 for (int ipq = 0; ipq < npq; ++ipq) {
                     double zeta, Px, Py, Pz, cpq;
@@ -368,17 +415,16 @@ rys_jk_thread_kernel(JKTask t)
                         cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
                     }
                     for (int irs = 0; irs < nrs; ++irs)
-                        jkt_prim_quartet<LP, LQ, LR, LS>(gout, zeta, Px, Py, Pz, cpq, Ax, Ay, Az, ABx, ABy, ABz,
-                                                         rsprim + irs * 5, Cx, Cy, Cz, CDx, CDy, CDz,
-                                                         t.omega, rys_tab);
+                        jkt_prim_quartet<LP, LQ, LR, LS, NCP>(gout, zeta, Px, Py, Pz, cpq, Ax, Ay, Az, ABx, ABy, ABz,
+                                                              rsprim + irs * 5, Cx, Cy, Cz, CDx, CDy, CDz,
+                                                              t.omega, rys_tab, c_lo);
                 }
 
-                // ---------------- digestion (thread-local) ----------------
+                // ---------------- digestion of this pass (thread-local) ----------------
 #pragma unroll
                 for (int idm = 0; idm < NDM; ++idm) {
                     const double *dm = t.dm + idm * nao2;
                     if (do_j) {
-                        double *vj = t.vj + idm * nao2;
 #pragma unroll
                         for (int a = 0; a < NFP; ++a)
 #pragma unroll
@@ -386,73 +432,103 @@ rys_jk_thread_kernel(JKTask t)
                             const double dpq = __ldg(dm + (size_t)(p0 + a) * nao + q0 + b);
                             double s = 0.;
 #pragma unroll
-                            for (int cd = 0; cd < NFRS; ++cd) {
-                                const double gv = gout[(a * NFQ + b) * NFRS + cd];
-                                s += gv * drs[idm * NFRS + cd];
-                                jacc[idm][cd] += gv * dpq;
+                            for (int cd = 0; cd < NCP * NFS; ++cd) {
+                                const double gv = gout[(a * NFQ + b) * NCP * NFS + cd];
+                                s += gv * drs[idm * NFRS + c_lo * NFS + cd];
+                                jacc[idm][c_lo * NFS + cd] += gv * dpq;
                             }
-                            JK_ATOMIC_ADD(vj + (size_t)(p0 + a) * nao + q0 + b, s);
+                            jpq[idm][a * NFQ + b] += s;
                         }
                     }
                     if (do_k) {
                         double *vk = t.vk + idm * nao2;
-                        // K_pr, K_ps (rows of p) and K_qr, K_qs (rows of q)
-                        double dqr[NFQ][NFR], dqs[NFQ][NFS];
+                        // K_pr (r components of this pass), K_ps (partial), rows of p
+                        double dqr[NFQ][NCP], dqs[NFQ][NFS];
 #pragma unroll
                         for (int b = 0; b < NFQ; ++b) {
-                            ld_row<NFR>(dqr[b], dm + (size_t)(q0 + b) * nao + r0, vec_r);
+                            if (NPART == 1) {
+                                ld_row<NCP>(dqr[b], dm + (size_t)(q0 + b) * nao + r0, vec_r);
+                            } else {
+#pragma unroll
+                                for (int cc = 0; cc < NCP; ++cc) dqr[b][cc] = __ldg(dm + (size_t)(q0 + b) * nao + r0 + c_lo + cc);
+                            }
                             ld_row<NFS>(dqs[b], dm + (size_t)(q0 + b) * nao + s0, vec_s);
                         }
 #pragma unroll
                         for (int a = 0; a < NFP; ++a) {
-                            double kpr[NFR], kps[NFS];
+                            double kpr[NCP];
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c) kpr[c] = 0.;
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) kps[d] = 0.;
+                            for (int cc = 0; cc < NCP; ++cc) kpr[cc] = 0.;
 #pragma unroll
                             for (int b = 0; b < NFQ; ++b)
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c)
+                            for (int cc = 0; cc < NCP; ++cc)
 #pragma unroll
                             for (int d = 0; d < NFS; ++d) {
-                                const double gv = gout[((a * NFQ + b) * NFR + c) * NFS + d];
-                                kpr[c] += gv * dqs[b][d];
-                                kps[d] += gv * dqr[b][c];
+                                const double gv = gout[((a * NFQ + b) * NCP + cc) * NFS + d];
+                                kpr[cc] += gv * dqs[b][d];
+                                kps[idm][a][d] += gv * dqr[b][cc];
                             }
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c) JK_ATOMIC_ADD(vk + (size_t)(p0 + a) * nao + r0 + c, kpr[c]);
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + (size_t)(p0 + a) * nao + s0 + d, kps[d]);
+                            for (int cc = 0; cc < NCP; ++cc)
+                                JK_ATOMIC_ADD(vk + (size_t)(p0 + a) * nao + r0 + c_lo + cc, kpr[cc]);
                         }
-                        double dpr[NFP][NFR], dps[NFP][NFS];
+                        // K_qr (r components of this pass), K_qs (partial), rows of q
+                        double dpr[NFP][NCP], dps[NFP][NFS];
 #pragma unroll
                         for (int a = 0; a < NFP; ++a) {
-                            ld_row<NFR>(dpr[a], dm + (size_t)(p0 + a) * nao + r0, vec_r);
+                            if (NPART == 1) {
+                                ld_row<NCP>(dpr[a], dm + (size_t)(p0 + a) * nao + r0, vec_r);
+                            } else {
+#pragma unroll
+                                for (int cc = 0; cc < NCP; ++cc) dpr[a][cc] = __ldg(dm + (size_t)(p0 + a) * nao + r0 + c_lo + cc);
+                            }
                             ld_row<NFS>(dps[a], dm + (size_t)(p0 + a) * nao + s0, vec_s);
                         }
 #pragma unroll
                         for (int b = 0; b < NFQ; ++b) {
-                            double kqr[NFR], kqs[NFS];
+                            double kqr[NCP];
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c) kqr[c] = 0.;
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) kqs[d] = 0.;
+                            for (int cc = 0; cc < NCP; ++cc) kqr[cc] = 0.;
 #pragma unroll
                             for (int a = 0; a < NFP; ++a)
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c)
+                            for (int cc = 0; cc < NCP; ++cc)
 #pragma unroll
                             for (int d = 0; d < NFS; ++d) {
-                                const double gv = gout[((a * NFQ + b) * NFR + c) * NFS + d];
-                                kqr[c] += gv * dps[a][d];
-                                kqs[d] += gv * dpr[a][c];
+                                const double gv = gout[((a * NFQ + b) * NCP + cc) * NFS + d];
+                                kqr[cc] += gv * dps[a][d];
+                                kqs[idm][b][d] += gv * dpr[a][cc];
                             }
 #pragma unroll
-                            for (int c = 0; c < NFR; ++c) JK_ATOMIC_ADD(vk + (size_t)(q0 + b) * nao + r0 + c, kqr[c]);
-#pragma unroll
-                            for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + (size_t)(q0 + b) * nao + s0 + d, kqs[d]);
+                            for (int cc = 0; cc < NCP; ++cc)
+                                JK_ATOMIC_ADD(vk + (size_t)(q0 + b) * nao + r0 + c_lo + cc, kqr[cc]);
                         }
+                    }
+                }
+                }   // passes over the r components
+
+                // ---------------- the sums over all r components leave the thread ----------------
+#pragma unroll
+                for (int idm = 0; idm < NDM; ++idm) {
+                    if (do_j) {
+                        double *vj = t.vj + idm * nao2;
+#pragma unroll
+                        for (int a = 0; a < NFP; ++a)
+#pragma unroll
+                        for (int b = 0; b < NFQ; ++b)
+                            JK_ATOMIC_ADD(vj + (size_t)(p0 + a) * nao + q0 + b, jpq[idm][a * NFQ + b]);
+                    }
+                    if (do_k) {
+                        double *vk = t.vk + idm * nao2;
+#pragma unroll
+                        for (int a = 0; a < NFP; ++a)
+#pragma unroll
+                        for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + (size_t)(p0 + a) * nao + s0 + d, kps[idm][a][d]);
+#pragma unroll
+                        for (int b = 0; b < NFQ; ++b)
+#pragma unroll
+                        for (int d = 0; d < NFS; ++d) JK_ATOMIC_ADD(vk + (size_t)(q0 + b) * nao + s0 + d, kqs[idm][b][d]);
                     }
                 }
             }   // lane < nb
