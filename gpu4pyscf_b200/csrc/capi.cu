@@ -105,7 +105,7 @@ static int build_class_impl(double *vj, double *vk, const double *dm, int n_dm, 
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
-                        double omega, double scale)
+                        double omega, double scale, double ratio2 = 0., double omega2 = 0.)
 {
     if (npair_x <= 0 || npair_y <= 0) return 0;
     if (RYS_b200_init()) return 1;
@@ -132,12 +132,14 @@ static int build_class_impl(double *vj, double *vk, const double *dm, int n_dm, 
     t.dedupe = dedupe;
     t.head = head;
     t.rec_y = rec_y;
-    if (omega < 0.) {
-        fprintf(stderr, "B200_build_jk_class: omega < 0 (short range) is composed on the host as full - long range\n");
+    if (omega < 0. || omega2 < 0.) {
+        fprintf(stderr, "B200_build_jk_class: omega < 0: the short-range operator is passed as two terms, 1/r and -erf(|omega| r)/r\n");
         return 1;
     }
     t.omega = omega;
     t.scale = scale;
+    t.ratio2 = ratio2;
+    t.omega2 = omega2;
     t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
     t.rank = rank;
     t.world = world < 1 ? 1 : world;
@@ -182,14 +184,14 @@ static int build_rows_impl(double *vj, double *vk, double *vkT, const double *dm
                            const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
                            const float *dm_cond, float cutoff, float dm_penalty,
                            int dedupe, int rank, int world, unsigned long long *head, void *stream,
-                           double omega, double scale)
+                           double omega, double scale, double ratio2 = 0., double omega2 = 0.)
 {
     if (npair_x <= 0 || nrows <= 0) return 0;
     if (RYS_b200_init()) return 1;
     int dev = rt_device();
     int lp = lprim[0], lq = lprim[1], lr = lprim[2], ls = lprim[3];
-    if (omega < 0.) {
-        fprintf(stderr, "B200_build_jk_rows: omega < 0 (short range) is composed by the caller\n");
+    if (omega < 0. || omega2 < 0.) {
+        fprintf(stderr, "B200_build_jk_rows: omega < 0: the short-range operator is passed as two terms\n");
         return 1;
     }
     if (rec_y == nullptr || (vk != nullptr && (vkT == nullptr || dmT == nullptr))) {
@@ -216,6 +218,8 @@ static int build_rows_impl(double *vj, double *vk, double *vkT, const double *dm
     t.rec_y = rec_y;
     t.omega = omega;
     t.scale = scale;
+    t.ratio2 = ratio2;
+    t.omega2 = omega2;
     t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
     t.rank = rank;
     t.world = world < 1 ? 1 : world;
@@ -280,11 +284,12 @@ int B200_build_jk_rows(double *vj, double *vk, double *vkT, const double *dm, co
                        const uint32_t *pair_y, const float *q_y, const double *rec_y,
                        const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
                        const float *dm_cond, float cutoff, float dm_penalty,
-                       int dedupe, int rank, int world, unsigned long long *head, void *stream, double omega)
+                       int dedupe, int rank, int world, unsigned long long *head, void *stream,
+                       double omega, double scale, double ratio2, double omega2)
 {
     return build_rows_impl(vj, vk, vkT, dm, dmT, n_dm, nao, envs, lprim, pair_x, q_x, npair_x,
                            pair_y, q_y, rec_y, row_ptr, row_p, row_qmax, nrows,
-                           dm_cond, cutoff, dm_penalty, dedupe, rank, world, head, stream, omega, 1.);
+                           dm_cond, cutoff, dm_penalty, dedupe, rank, world, head, stream, omega, scale, ratio2, omega2);
 }
 
 int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
@@ -293,11 +298,19 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
-                        double omega)
+                        double omega, double scale, double ratio2, double omega2)
 {
     return build_class_impl(vj, vk, dm, n_dm, nao, envs, lprim, pair_x, q_x, npair_x, pair_y, q_y, npair_y,
                             dm_cond, cutoff, dm_penalty, q_margin, dedupe, rank, world, head, stream, rec_y,
-                            omega, 1.);
+                            omega, scale, ratio2, omega2);
+}
+
+// 1 if the kernel family serving the class evaluates two operator terms in one pass (thread-per-quartet
+// kernels and the flat warp-team kernel; the row-stream warp kernel and the block kernel take one term)
+int B200_class_two_terms(int lp, int lq, int lr, int ls, int row)
+{
+    const int kind = B200_class_kind(lp, lq, lr, ls, row);
+    return kind == 1 || (kind == 2 && !row);
 }
 
 // One group quadruple with the reference's (ij|kl) argument order; scale multiplies the integrals.
@@ -305,7 +318,7 @@ static int build_group(double *vj, double *vk, double *dm, int n_dm, int nao, Ry
                        int *shls_slice, int npairs_ij, int npairs_kl,
                        uint32_t *pair_ij_mapping, uint32_t *pair_kl_mapping, float *q_cond_ij, float *q_cond_kl,
                        float *dm_cond, float cutoff, float dm_penalty, uint32_t *pool, int *bas,
-                       double omega, double scale)
+                       double omega, double scale, double ratio2 = 0., double omega2 = 0.)
 {
     int ish0 = shls_slice[0], jsh0 = shls_slice[2], ksh0 = shls_slice[4], lsh0 = shls_slice[6];
     int li = bas[ish0 * BAS_SLOTS + ANG_OF], lj = bas[jsh0 * BAS_SLOTS + ANG_OF];
@@ -323,12 +336,23 @@ static int build_group(double *vj, double *vk, double *dm, int n_dm, int nao, Ry
         int lprim[8] = {li, lj, lk, ll, ni, nj, nk, nl};
         return build_class_impl(vj, vk, dm, n_dm, nao, envs, lprim,
                                 pair_kl_mapping, q_cond_kl, npairs_kl, pair_ij_mapping, q_cond_ij, npairs_ij,
-                                dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr, nullptr, omega, scale);
+                                dm_cond, cutoff, dm_penalty, 4.f, 3, 0, 1, head, nullptr, nullptr, omega, scale,
+                                ratio2, omega2);
     }
     int lprim[8] = {lk, ll, li, lj, nk, nl, ni, nj};
     return build_class_impl(vj, vk, dm, n_dm, nao, envs, lprim,
                             pair_ij_mapping, q_cond_ij, npairs_ij, pair_kl_mapping, q_cond_kl, npairs_kl,
-                            dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr, nullptr, omega, scale);
+                            dm_cond, cutoff, dm_penalty, 4.f, 2, 0, 1, head, nullptr, nullptr, omega, scale,
+                            ratio2, omega2);
+}
+
+// does the kernel of this group quadruple take two operator terms in one pass?
+static int group_two_terms(const int *shls_slice, const int *bas)
+{
+    int li = bas[shls_slice[0] * BAS_SLOTS + ANG_OF], lj = bas[shls_slice[2] * BAS_SLOTS + ANG_OF];
+    int lk = bas[shls_slice[4] * BAS_SLOTS + ANG_OF], ll = bas[shls_slice[6] * BAS_SLOTS + ANG_OF];
+    if (B200_has_class(li, lj, lk, ll)) return B200_class_two_terms(li, lj, lk, ll, 0);
+    return B200_class_two_terms(lk, ll, li, lj, 0);
 }
 
 int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
@@ -348,6 +372,10 @@ int RYS_build_jk(double *vj, double *vk, double *dm, int n_dm, int nao,
         return build_group(vj, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
                            pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
                            dm_cond, cutoff, dm_penalty, pool, bas, omega, 1.);
+    if (group_two_terms(shls_slice, bas))       // 1/r - erf(|omega| r)/r in one pass
+        return build_group(vj, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
+                           pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
+                           dm_cond, cutoff, dm_penalty, pool, bas, 0., 1., -1., -omega);
     int err = build_group(vj, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
                           pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
                           dm_cond, cutoff, dm_penalty, pool, bas, 0., 1.);
@@ -380,6 +408,10 @@ int RYS_build_k(double *vk, double *dm, int n_dm, int nao, double omega, double 
         c_lr = lr_factor - sr_factor;
     }
     const double w = omega < 0. ? -omega : omega;
+    if (c_full != 0. && c_lr != 0. && group_two_terms(shls_slice, bas))      // both terms in one pass
+        return build_group(nullptr, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
+                           pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,
+                           dm_cond, cutoff, dm_penalty, pool, bas, 0., c_full, c_lr / c_full, w);
     if (c_full != 0.) {
         int err = build_group(nullptr, vk, dm, n_dm, nao, envs, shls_slice, npairs_ij, npairs_kl,
                               pair_ij_mapping, pair_kl_mapping, q_cond_ij, q_cond_kl,

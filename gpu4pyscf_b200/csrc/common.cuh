@@ -70,6 +70,11 @@ struct JKTask {
     int slot_doubles;       // shared-memory doubles per slot
     double scale;           // factor applied to every integral (lr/sr mixing of RYS_build_k); 1 by default
     double omega;           // 0: 1/r; > 0: long-range erf(omega r)/r (reference: rys_roots_rs, rys_roots.cu:91-119)
+    // optional second operator term evaluated in the same pass (range-separated exchange in ONE build:
+    // the reference concatenates the full-range and the negated long-range roots, rys_roots_for_k.cu:45-60):
+    // integral = scale * ( O[omega] + ratio2 * O[omega2] ),  ratio2 == 0: single term
+    double ratio2;
+    double omega2;
     const double *rec_y;    // optional per-pair records of the Y list (pair_record_kernel), or null
     int rec_stride;         // doubles per record
     int ychunk;             // work item = (X pair, chunk of `ychunk` consecutive Y candidates)

@@ -140,9 +140,10 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         return 1;
     }
     int nteams = jkw_block_threads(C::TEAM, C::TILE * (1 + NDM)) / C::TEAM;
-    const int nprimq = npq * nrs;
+    const int nterm = t->ratio2 != 0. ? 2 : 1;       // operator terms evaluated in this pass
+    const int nprimq = npq * nrs * nterm;
     if ((BL || ROW) && nprimq != 1) {
-        fprintf(stderr, "rys_jk_warp: the b-loop and row-stream variants only handle uncontracted launches\n");
+        fprintf(stderr, "rys_jk_warp: the b-loop and row-stream variants only handle uncontracted single-operator launches\n");
         return 1;
     }
     // g-sets per lane slot: fill (not overfill) the team in the root/recurrence phase,
@@ -159,7 +160,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     const int rowd = ROW ? 2 * NDM * C::NFP * (C::NFR + C::NFS) : 0;
     auto smem_of = [&](int k) {
         return (RysSmem<C::NROOTS>::DOUBLES
-                + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET, rowd, C::redd(ROW))) * 8;
+                + nteams * jkw_team_doubles(C::TEAM, C::NSW, k, npq, nrs, NDM, C::NFRS, C::GSET, rowd, C::redd(ROW), nterm)) * 8;
     };
     const int budget = (smem_max + 1024) / minb - 1024;
     while (!ROW && K > 1 && smem_of(K) > budget) --K;
@@ -171,7 +172,7 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
         return 1;
     }
     t->nq = K;
-    t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET, rowd, C::redd(ROW));
+    t->slot_doubles = jkw_team_doubles(C::TEAM, C::NSW, K, npq, nrs, NDM, C::NFRS, C::GSET, rowd, C::redd(ROW), nterm);
     int per_sm = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL, ROW>, smem, nt);
     if (per_sm < 1) {
         fprintf(stderr, "rys_jk_warp: class (%d%d|%d%d) cannot be made resident (smem %d, threads %d)\n",

@@ -279,10 +279,15 @@ rys_jk_rowt_kernel(JKTask t)
                         const double *pr = rec + PAIR_REC_HDR + ipq * 5;
                         const double zeta = pr[0], Px = pr[1], Py = pr[2], Pz = pr[3];
                         const double cpq = fac * pr[4];
-                        for (int irs = 0; irs < nrs; ++irs)
+                        for (int irs = 0; irs < nrs; ++irs) {
                             jkt_prim_quartet<LP, LQ, LR, LS>(gout, zeta, Px, Py, Pz, cpq, Ax, Ay, Az, ABx, ABy, ABz,
                                                              rsprim + irs * 5, Cx, Cy, Cz, CDx, CDy, CDz,
                                                              t.omega, rys_tab);
+                            if (t.ratio2 != 0.)      // second operator term into the same integrals
+                                jkt_prim_quartet<LP, LQ, LR, LS>(gout, zeta, Px, Py, Pz, cpq * t.ratio2, Ax, Ay, Az,
+                                                                 ABx, ABy, ABz, rsprim + irs * 5, Cx, Cy, Cz,
+                                                                 CDx, CDy, CDz, t.omega2, rys_tab);
+                        }
                     }
 
                     // ---------------- digestion: q is the column index of every global access ----------------

@@ -414,10 +414,15 @@ rys_jk_thread_kernel(JKTask t)
                         Px = Ax - fq * ABx; Py = Ay - fq * ABy; Pz = Az - fq * ABz;
                         cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
                     }
-                    for (int irs = 0; irs < nrs; ++irs)
+                    for (int irs = 0; irs < nrs; ++irs) {
                         jkt_prim_quartet<LP, LQ, LR, LS, NCP>(gout, zeta, Px, Py, Pz, cpq, Ax, Ay, Az, ABx, ABy, ABz,
                                                               rsprim + irs * 5, Cx, Cy, Cz, CDx, CDy, CDz,
                                                               t.omega, rys_tab, c_lo);
+                        if (t.ratio2 != 0.)      // second operator term into the same integrals
+                            jkt_prim_quartet<LP, LQ, LR, LS, NCP>(gout, zeta, Px, Py, Pz, cpq * t.ratio2, Ax, Ay, Az,
+                                                                  ABx, ABy, ABz, rsprim + irs * 5, Cx, Cy, Cz,
+                                                                  CDx, CDy, CDz, t.omega2, rys_tab, c_lo);
+                    }
                 }
 
                 // ---------------- digestion of this pass (thread-local) ----------------

@@ -157,10 +157,11 @@ struct JKWCfg : JKCfg<LP, LQ, LR, LS, NCS> {
 // rowd: doubles of the row buffers of the row-stream variant (D_p* block + K_p* accumulators), else 0
 // redd: doubles of the reduction scratch (JKWCfg::redd), even
 __host__ __device__ inline int jkw_team_doubles(int team_threads, int nsw, int K, int npq, int nrs,
-                                                int ndm, int nfrs, int gset, int rowd = 0, int redd = 0)
+                                                int ndm, int nfrs, int gset, int rowd = 0, int redd = 0,
+                                                int nterm = 1)
 {
     int ngs = nsw * K;
-    int nqs = (npq * nrs == 1) ? ngs : nsw;
+    int nqs = (npq * nrs * nterm == 1) ? ngs : nsw;
     int qcap = nqs + team_threads;
     int n = 8 + nrs * 5 + ndm * nfrs + rowd + (qcap + 1) / 2 + nqs * (JKW_SLOT_HDR + 5 * npq);
     n = (n + 1) & ~1;                    // g-sets start 16-byte aligned
@@ -269,7 +270,10 @@ rys_jk_warp_kernel(JKTask t)
     constexpr bool SNG = ROW != 0;
     const int npq = SNG ? 1 : t.nprim_p * t.nprim_q;
     const int nrs = SNG ? 1 : t.nprim_r * t.nprim_s;
-    const int nprimq = npq * nrs;
+    // a second operator term (JKTask::ratio2) doubles the primitive-quartet list: entry pi of
+    // [nprimq, 2 nprimq) is primitive quartet pi - nprimq evaluated with omega2 and weight * ratio2
+    const int nterm = (!SNG && t.ratio2 != 0.) ? 2 : 1;
+    const int nprimq = npq * nrs * nterm;
     const bool single = SNG || nprimq == 1;
     const int K = SNG ? C::KROW : t.nq;      // g-sets per lane slot
     const int ngs = NSW * K;
@@ -694,6 +698,9 @@ rys_jk_warp_kernel(JKTask t)
                     }
                     const bool valid = pi < nprimq;
                     if (!valid) pi = 0;
+                    const bool term2 = pi >= npq * nrs;
+                    if (term2) pi -= npq * nrs;
+                    const double om = term2 ? t.omega2 : t.omega;
                     const int ipq = pi / nrs;
                     const int irs = pi - ipq * nrs;
                     const double *sl = slots + j * slot_d;
@@ -708,8 +715,9 @@ rys_jk_warp_kernel(JKTask t)
                     double x = theta * (dx * dx + dy * dy + dz * dz);
                     double rscale = rze;
                     double w = valid ? sl[6] * pp[4] * rr[4] * ize * rsq : 0.;
-                    if (t.omega != 0.) {                            // long range: theta -> theta * lrf
-                        const double lrf = t.omega * t.omega / (t.omega * t.omega + theta);
+                    if (term2) w *= t.ratio2;
+                    if (om != 0.) {                                 // long range: theta -> theta * lrf
+                        const double lrf = om * om / (om * om + theta);
                         x *= lrf;
                         rscale *= lrf;
                         w *= sqrt(lrf);

@@ -168,6 +168,35 @@ def _lpt_owners(cost, world, split_min=float('inf')):
     return owners
 
 
+class _PairLists:
+    '''Screening data of one operator: per group pair (ids, q, s, records), the row views, the launch
+    plan and the measured launch times of the multi-GPU partition.'''
+    def __init__(self):
+        self.cache = None
+        self.rows = {}
+        self.tasks = None
+        self.qmax = None
+        self.launch_cost = None
+
+
+def _estimator_operator(terms):
+    '''(omega, lr_factor, sr_factor) in the convention of int2e_qcond_estimator for the operator
+    sum_k coef_k O[w_k], O[0] = 1/r, O[w] = erf(w r)/r: one term, or (c_full, 0) + (c_lr, w).'''
+    if len(terms) == 1:
+        c, w = terms[0]
+        return (0., abs(c), abs(c)) if w == 0 else (w, abs(c), 0.)
+    (c0, w0), (c1, w1) = terms
+    assert w0 == 0 and w1 > 0
+    return (-w1, c1 + c0, c0)          # sr = c_full, lr = c_lr + c_full
+
+
+def _psd_pair(terms):
+    '''can the two terms be screened with the Schwarz bound of their SUM?  Needs a positive
+    semi-definite operator: lr*erf/r + sr*erfc/r with lr, sr >= 0'''
+    (c0, w0), (c1, w1) = terms
+    return w0 == 0 and w1 > 0 and c0 > 0 and c1 + c0 >= 0
+
+
 class _VHFOpt:
     '''Screening object of the direct-SCF J/K build (reference: jk.py:407-927).'''
 
@@ -177,9 +206,13 @@ class _VHFOpt:
         self.tile = tile
         self.sorted_mol = None
         self.h_shls = []
-        self.bas_pair_cache = None
         self._rys_envs = None
         self.device = None
+        # screening lists per operator: key = ((coef, w), ...) of the operator terms -> _PairLists; `_cur`
+        # is the set the current pass works on (the molecule's own operator after build())
+        self._lists = {}
+        self._cur = _PairLists()
+        self._default = None
         # multi-GPU partition (set by the caller or picked up from torch.distributed)
         self.rank = None
         self.world = None
@@ -192,21 +225,41 @@ class _VHFOpt:
         # row-stream kernels are used when the streamed list has rows at least this long on average
         self.row_min = float(os.environ.get('B200_ROW_MIN', '24'))
         self._streams = None
-        self._tasks = None
-        self._qmax_cache = None
-        self._rows = {}
-        self._launch_cost = None      # measured GPU ms per class launch (multi-GPU cost partition)
+
+    # the attributes of the reference object (bas_pair_cache) and the launch plan derived from it
+    # live in the _PairLists of the operator in use
+    # bas_pair_cache (reference attribute): the lists of the molecule's own operator, whatever pass ran last
+    bas_pair_cache = property(lambda self: self._default.cache if self._default is not None else None)
+    _rows = property(lambda self: self._cur.rows, lambda self, v: setattr(self._cur, 'rows', v))
+    _tasks = property(lambda self: self._cur.tasks, lambda self, v: setattr(self._cur, 'tasks', v))
+    _qmax_cache = property(lambda self: self._cur.qmax, lambda self, v: setattr(self._cur, 'qmax', v))
+    _launch_cost = property(lambda self: self._cur.launch_cost,
+                            lambda self, v: setattr(self._cur, 'launch_cost', v))
 
     def reset(self, mol):
         self.mol = mol
         self.sorted_mol = None
-        self.bas_pair_cache = None
         self._rys_envs = None
-        self._tasks = None
-        self._qmax_cache = None
-        self._rows = {}
-        self._launch_cost = None
+        self._lists = {}
+        self._cur = _PairLists()
+        self._default = None
         return self
+
+    def _use_lists(self, terms):
+        '''Make the screening lists of the operator sum_k coef_k O[w_k] current, building them on first
+        use: Schwarz bounds of THAT operator (reference: _VHFOpt.build under mol.with_range_coulomb(omega),
+        hf.py:936-944, computes q_cond with the attenuated operator), pair lists, launch plan.'''
+        key = tuple((float(c), float(w)) for c, w in terms)
+        pl = self._lists.get(key)
+        if pl is None:
+            lib = loader.load_library()
+            pl = _PairLists()
+            pl.cache = _cache_q_cond_and_non0pairs(
+                self.sorted_mol, self._rys_envs, self.direct_scf_tol, self.device, lib, self.q_bin,
+                _estimator_operator(key))
+            self._lists[key] = pl
+        self._cur = pl
+        return pl
 
     # ------------------------------------------------------------------
     def build(self, group_size=None, verbose=None):
@@ -222,11 +275,8 @@ class _VHFOpt:
                 f'shells with l > {LMAX} are not supported on the GPU and this '
                 'implementation has no CPU fallback')
         self._make_rys_envs()
-        self.bas_pair_cache = _cache_q_cond_and_non0pairs(
-            smol, self._rys_envs, self.direct_scf_tol, self.device, lib, self.q_bin)
-        self._rows = {}
-        self._tasks = None
-        self._launch_cost = None
+        self._lists = {}
+        self._default = self._use_lists(self._own_terms() or [(1., 0.)])
         return self
 
     def _make_rys_envs(self):
@@ -274,7 +324,7 @@ class _VHFOpt:
         uniq = smol.uniq_l_ctr
         counts = np.asarray(smol.l_ctr_counts)
         gi, gj = key
-        ids, q = self.bas_pair_cache[key][:2]
+        ids, q = self._cur.cache[key][:2]
         li, lj = int(uniq[gi, 0]), int(uniq[gj, 0])
         stream_second = li > lj or counts[gj] >= counts[gi]
         gp, gq = (gi, gj) if stream_second else (gj, gi)
@@ -318,7 +368,7 @@ class _VHFOpt:
         lib = loader.load_library()
         smol = self.sorted_mol
         uniq = smol.uniq_l_ctr
-        keys = sorted(self.bas_pair_cache.keys())
+        keys = sorted(self._cur.cache.keys())
         use_rows = os.environ.get('B200_ROWS', '1') == '1'
 
         def ls(key):
@@ -327,7 +377,7 @@ class _VHFOpt:
         def row_score(ky, kx):
             '''cost estimate of streaming ky through its row view against resident kx (lower is
             better), or None when no row-stream kernel serves the launch / rows are too short'''
-            if not use_rows or len(self.bas_pair_cache[ky][0]) == 0:
+            if not use_rows or len(self._cur.cache[ky][0]) == 0:
                 return None
             rl = self.row_list(ky)
             if rl['mean_len'] < self.row_min:
@@ -376,12 +426,17 @@ class _VHFOpt:
         return tasks
 
     # ------------------------------------------------------------------
-    def _jk_pass(self, dms, hermi, with_j, with_k, omega):
-        '''One pass over all quartets with the operator 1/r (omega = 0) or erf(omega r)/r
-        (omega > 0): J/K in the sorted Cartesian basis, symmetrised as the reference does
-        (jk.py:594-616).  dms: (n_dm, nao, nao) device tensor.  Returns (vj, vk), None where not
+    def _jk_pass(self, dms, hermi, with_j, with_k, terms):
+        '''One pass over all quartets with the operator sum_k coef_k O[w_k] (O[0] = 1/r, O[w > 0] =
+        erf(w r)/r; one term, or 1/r plus an erf term: range-separated exchange in ONE build, the
+        counterpart of the reference's doubled root set, rys_roots_for_k.cu:45-60), screened with the
+        Schwarz bounds of that operator: J/K in the sorted Cartesian basis, symmetrised as the reference
+        does (jk.py:594-616).  dms: (n_dm, nao, nao) device tensor.  Returns (vj, vk), None where not
         requested.'''
-        assert omega >= 0
+        if isinstance(terms, (int, float)):
+            terms = [(1., float(terms))]
+        assert 1 <= len(terms) <= 2 and all(w >= 0 for _, w in terms)
+        self._use_lists(terms)
         lib = loader.load_library()
         smol = self.sorted_mol
         dev = self.device
@@ -427,7 +482,9 @@ class _VHFOpt:
         # launch times (items dealt, launches serialised, CUDA events) and ships them in the tail of the
         # [vj|vk] buffer, so there is still ONE all_reduce per build.
         part = os.environ.get('B200_PARTITION', 'hybrid')
-        cost_mode = world > 1 and part in ('cost', 'hybrid') and self.class_timing is None
+        # (a caller that sets rank/world by hand drives the ranks itself: plain item dealing, no shared state)
+        spmd = self.world is None and torch.distributed.is_available() and torch.distributed.is_initialized()
+        cost_mode = world > 1 and spmd and part in ('cost', 'hybrid') and self.class_timing is None
         measuring = cost_mode and (self._launch_cost is None or len(self._launch_cost) != len(tasks))
         owners = None
         if cost_mode and not measuring:
@@ -459,7 +516,7 @@ class _VHFOpt:
 
         if getattr(self, 'counter', None) is not None:
             self._counter_last = int(self.counter.item())
-        heads = torch.zeros(len(tasks) + 1, dtype=torch.int64, device=dev)
+        heads = torch.zeros(2 * len(tasks) + 1, dtype=torch.int64, device=dev)
         if side is not None:
             ev = torch.cuda.Event()
             ev.record(main)
@@ -470,8 +527,8 @@ class _VHFOpt:
         timers = []
         only = getattr(self, 'only_classes', None)   # measurement: restrict to some classes
         for it, (mode, ky, kx, dedupe) in enumerate(tasks):
-            pair_x, q_x = self.bas_pair_cache[kx][:2]
-            if len(pair_x) == 0 or len(self.bas_pair_cache[ky][0]) == 0:
+            pair_x, q_x = self._cur.cache[kx][:2]
+            if len(pair_x) == 0 or len(self._cur.cache[ky][0]) == 0:
                 continue
             # cheap class-level early exit
             if float(self._qmax[kx]) + float(self._qmax[ky]) + dm_penalty < cutoff:
@@ -487,7 +544,6 @@ class _VHFOpt:
             if only is not None:
                 if tuple(lprim[:4]) not in only and tuple(lprim) not in only:
                     continue
-            head = ctypes.c_void_p(heads.data_ptr() + 8 * it)
             l_rank, l_world = rank, world
             if owners is not None and owners[it] >= 0:
                 if owners[it] != rank:
@@ -506,21 +562,32 @@ class _VHFOpt:
                 ev0.record()
             if side is not None:
                 stream = ctypes.c_void_p(side[it % len(side)].cuda_stream)
-            if mode == 'row':
-                err = lib.B200_build_jk_rows(
-                    _ptr(vj), _ptr(vk), _ptr(vkT), _ptr(dms), _ptr(dmT), ndm_k, nao, ctypes.byref(envs), lprim,
-                    _ptr(pair_x), _ptr(q_x), len(pair_x),
-                    _ptr(rl['pair']), _ptr(rl['q']), _ptr(rl['rec']),
-                    _ptr(rl['row_ptr']), _ptr(rl['row_p']), _ptr(rl['row_qmax']), rl['nrows'],
-                    _ptr(dm_cond), cutoff, dm_penalty, dedupe, l_rank, l_world, head, stream, float(omega))
+            # operator of the launch: both terms at once where the kernel family takes them, else one
+            # launch per term into the same outputs
+            if len(terms) == 2 and lib.B200_class_two_terms(lprim[0], lprim[1], lprim[2], lprim[3], int(mode == 'row')):
+                ops = [(terms[0][1], terms[0][0], terms[1][0] / terms[0][0], terms[1][1])]
             else:
-                pair_y, q_y = self.bas_pair_cache[ky][:2]
-                rec_y = self.bas_pair_cache[ky][3]
-                err = lib.B200_build_jk_class(
-                    _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
-                    _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
-                    _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, l_rank, l_world, head, stream,
-                    _ptr(rec_y), float(omega))
+                ops = [(w, c, 0., 0.) for c, w in terms]
+            for iop, (op_w, op_scale, op_ratio2, op_w2) in enumerate(ops):
+                head = ctypes.c_void_p(heads.data_ptr() + 8 * (2 * it + iop))
+                if mode == 'row':
+                    err = lib.B200_build_jk_rows(
+                        _ptr(vj), _ptr(vk), _ptr(vkT), _ptr(dms), _ptr(dmT), ndm_k, nao, ctypes.byref(envs), lprim,
+                        _ptr(pair_x), _ptr(q_x), len(pair_x),
+                        _ptr(rl['pair']), _ptr(rl['q']), _ptr(rl['rec']),
+                        _ptr(rl['row_ptr']), _ptr(rl['row_p']), _ptr(rl['row_qmax']), rl['nrows'],
+                        _ptr(dm_cond), cutoff, dm_penalty, dedupe, l_rank, l_world, head, stream,
+                        float(op_w), float(op_scale), float(op_ratio2), float(op_w2))
+                else:
+                    pair_y, q_y = self._cur.cache[ky][:2]
+                    rec_y = self._cur.cache[ky][3]
+                    err = lib.B200_build_jk_class(
+                        _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
+                        _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
+                        _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, l_rank, l_world, head, stream,
+                        _ptr(rec_y), float(op_w), float(op_scale), float(op_ratio2), float(op_w2))
+                if err:
+                    break
             if err:
                 raise RuntimeError('J/K launch failed for class %s (%s)' % (tuple(lprim), mode))
             if measuring:
@@ -536,7 +603,7 @@ class _VHFOpt:
                 rec = self.class_timing.setdefault(key, [0., 0, 0, 0])
                 rec[0] += ev0.elapsed_time(ev1)
                 rec[1] += len(pair_x)
-                rec[2] += len(self.bas_pair_cache[ky][0])
+                rec[2] += len(self._cur.cache[ky][0])
                 if getattr(self, 'counter', None) is not None:
                     n = int(self.counter.item())
                     rec[3] += n - self._counter_last
@@ -580,15 +647,18 @@ class _VHFOpt:
         return vj, vk
 
     def _combine(self, dms, hermi, with_j, with_k, terms):
-        '''sum of coefficient * pass over the operator terms [(coef, w)]'''
+        '''J/K of the operator sum_k coef_k O[w_k]: ONE pass when the sum is positive semi-definite (its own
+        Schwarz bounds are valid for it), else one pass per term'''
+        if len(terms) == 0:
+            return None, None
+        if len(terms) == 1 or _psd_pair(terms):
+            return self._jk_pass(dms, hermi, with_j, with_k, list(terms))
         vj = vk = None
-        for coef, w in terms:
-            tj, tk = self._jk_pass(dms, hermi, with_j, with_k, w)
+        for term in terms:
+            tj, tk = self._jk_pass(dms, hermi, with_j, with_k, [term])
             if tj is not None:
-                tj = tj if coef == 1 else tj * coef
                 vj = tj if vj is None else vj + tj
             if tk is not None:
-                tk = tk if coef == 1 else tk * coef
                 vk = tk if vk is None else vk + tk
         return vj, vk
 
@@ -623,7 +693,7 @@ class _VHFOpt:
     def _qmax(self):
         if getattr(self, '_qmax_cache', None) is None:
             self._qmax_cache = {k: (float(v[1].max()) if len(v[1]) else -1e30)
-                                for k, v in self.bas_pair_cache.items()}
+                                for k, v in self._cur.cache.items()}
         return self._qmax_cache
 
 
@@ -644,14 +714,15 @@ def _diffuse_pgto_params(smol):
     return exps, cs
 
 
-def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib, q_bin=0.):
+def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib, q_bin=0., operator=(0., 1., 1.)):
     '''Per group pair (gi >= gj): shell-pair ids ``ish*nbas+jsh`` (ish >= jsh), their Schwarz
     bounds q = 1/2 log max|(ij|ij)|, the same again as ``s_cond`` and the Gaussian-product
     records -- same role and call sequence as the reference (scf/jk.py:984-1120):
 
     1. overlap prescreen + enumeration of all ish >= jsh pairs in one kernel
        (``B200_pair_prescreen``: count pass, prefix sum, fill pass),
-    2. ONE ``int2e_qcond_estimator`` launch sequence over the concatenated list (reference signature),
+    2. ONE ``int2e_qcond_estimator`` launch sequence over the concatenated list (reference signature) with
+       ``operator`` = (omega, lr_factor, sr_factor) of the operator the lists will screen,
     3. one global sort by (group pair, q bin descending, pair id) -- the reference bins by 4 log
        units (Q_COND_MARGIN); here the bins are ``q_bin`` wide (0: exactly q-sorted), and pairs
        that cannot survive against the largest bound of the molecule are dropped,
@@ -696,7 +767,7 @@ def _cache_q_cond_and_non0pairs(smol, rys_envs, precision, device, lib, q_bin=0.
     if device.type == 'cuda':
         torch.cuda.current_stream().synchronize()
     if lib.int2e_qcond_estimator(_ptr(q), ctypes.byref(rys_envs), 0, len(spo) - 1, _ptr(ids), _ptr(spo_d),
-                                 None, 0., 1., 1.):
+                                 None, float(operator[0]), float(operator[1]), float(operator[2])):
         raise RuntimeError('int2e_qcond_estimator kernel failed')
     if device.type == 'cuda':
         torch.cuda.synchronize()

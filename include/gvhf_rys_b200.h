@@ -93,9 +93,9 @@ int RYS_build_k(double *vk, double *dm, int n_dm, int nao, double omega, double 
  *   partition of the q-sorted list); head: zeroed device int work counter.
  *   rec_y: optional per-pair records of the Y list (B200_pair_records), NULL to
  *   derive the Gaussian products from bas/env inside the kernel.
- *   omega: 0 for 1/r, > 0 for the long-range operator erf(omega r)/r (reference:
- *   rys_roots_rs, lib/gvhf-rys/rys_roots.cu:91-119); the short-range operator is
- *   composed on the host as full - long range, so omega < 0 is rejected here.
+ *   omega, scale, ratio2, omega2: the operator, see B200_class_two_terms below (omega = 0 for 1/r, > 0
+ *   for the long-range operator erf(omega r)/r, reference rys_roots_rs, lib/gvhf-rys/rys_roots.cu:91-119;
+ *   negative values are rejected: the short-range operator is a two-term operator).
  * vj or vk may be NULL (K-only / J-only).  n_dm is arbitrary. */
 int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
                         const RysIntEnvVars *envs, const int *lprim,
@@ -103,7 +103,7 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
-                        double omega);
+                        double omega, double scale, double ratio2, double omega2);
 
 /* Native entry, row-stream kernels (csrc/rys_jk_rowt.cuh, ROW variant of rys_jk_warp.cuh): one
  * angular class with the streamed list grouped in ROWS of one shell p.
@@ -124,7 +124,15 @@ int B200_build_jk_rows(double *vj, double *vk, double *vkT, const double *dm, co
                        const uint32_t *pair_y, const float *q_y, const double *rec_y,
                        const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
                        const float *dm_cond, float cutoff, float dm_penalty,
-                       int dedupe, int rank, int world, unsigned long long *head, void *stream, double omega);
+                       int dedupe, int rank, int world, unsigned long long *head, void *stream,
+                       double omega, double scale, double ratio2, double omega2);
+
+/* Operator of a native launch: every integral is  scale * ( O[omega] + ratio2 * O[omega2] )  with O[0] = 1/r and
+ * O[w > 0] = erf(w r)/r; ratio2 = 0 is a single term.  The short-range operator erfc(w r)/r is (omega = 0,
+ * ratio2 = -1, omega2 = w): the counterpart of the reference's doubled root set (rys_roots_for_k.cu:45-60).
+ * B200_class_two_terms: 1 if the kernel family that serves the class takes both terms in one pass (else the
+ * caller issues one launch per term). */
+int B200_class_two_terms(int lp, int lq, int lr, int ls, int row);
 
 /* 1 if a row-stream kernel is instantiated for rows of (lp,lq) pairs against resident (lr,ls) pairs. */
 int B200_has_row_class(int lp, int lq, int lr, int ls);

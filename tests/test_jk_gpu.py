@@ -469,3 +469,37 @@ def test_pair_prescreen_is_conservative():
                                   loader.current_stream_ptr()) == 0
             worst = max(worst, float(q.max()))
     assert worst + qmax < math.log(1e-13), (worst, qmax)
+
+
+def test_short_range_single_pass_with_g_shells_and_screening():
+    """Short-range K in ONE build (two operator terms per quartet, the counterpart of the reference's doubled
+    root set, rys_roots_for_k.cu:45-60) screened with the short-range Schwarz bounds: (a) the inline l <= 4
+    molecule, where the block kernel of the (gx|gg) classes takes one launch per term; (b) an 8-atom Taxol
+    fragment with a decaying density, so that the SR-specific pair lists and the density screening are active.
+    Oracle evaluated without screening."""
+    from gpu4pyscf_b200.scf import jk
+    oracle = _oracle()
+    mol = molecules.mol1_lmax(4)
+    np.random.seed(21)
+    dm = np.random.rand(mol.nao, mol.nao)
+    dm = dm + dm.T
+    vk = jk.get_k(mol, dm, hermi=1, omega=-0.3).cpu().numpy()
+    rk = oracle.get_jk(mol, dm, hermi=1, omega=-0.3)[1]
+    assert abs(vk - rk).max() < 1e-10
+
+    mol = _taxol(8)
+    dm = _decaying_density(mol)
+    opt = jk._VHFOpt(mol).build()
+    vk = jk.get_k(mol, dm, hermi=1, vhfopt=opt, omega=-0.4).cpu().numpy()
+    rk = oracle.get_jk(mol, dm, hermi=1, omega=-0.4)[1]
+    assert abs(vk - rk).max() < 1e-10
+    # the SR lists are screened with the SR bounds: never more pairs than the full-range lists
+    full = sum(len(v[0]) for v in opt._lists[((1., 0.),)].cache.values())
+    sr = sum(len(v[0]) for v in opt._lists[((1., 0.), (-1., 0.4))].cache.values())
+    assert 0 < sr <= full
+    # and bas_pair_cache keeps pointing at the molecule's own operator
+    assert sum(len(v[0]) for v in opt.bas_pair_cache.values()) == full
+    # mixed factors (omega-B97-type: lr 1.0, sr 0.157 -> sr*1/r + (lr - sr)*erf): one pass as well
+    vk = jk.get_k(mol, dm, hermi=1, vhfopt=opt, omega=0.3, lr_factor=1., sr_factor=0.157706).cpu().numpy()
+    rk = (oracle.get_jk(mol, dm, hermi=1, omega=0.3)[1] + 0.157706 * oracle.get_jk(mol, dm, hermi=1, omega=-0.3)[1])
+    assert abs(vk - rk).max() < 1e-10

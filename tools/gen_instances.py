@@ -231,7 +231,7 @@ def main(dst):
                                 bl = None
                         if bl is not None:
                             f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
-                                    '{\n    if (t->nprim_p * t->nprim_q * t->nprim_r * t->nprim_s == 1)\n'
+                                    '{\n    if (t->nprim_p * t->nprim_q * t->nprim_r * t->nprim_s == 1 && t->ratio2 == 0.)\n'
                                     '        return jk_launch_warp<%d, %d, %d, %d, %d, %d, 1>(t, nsm, smem_max, s);\n'
                                     '    return jk_launch_warp<%d, %d, %d, %d, %d, %d>(t, nsm, smem_max, s);\n}\n'
                                     % (name, lp, lq, lr, ls, bl[1], ndm, lp, lq, lr, ls, wc[1], ndm))
@@ -265,7 +265,7 @@ def main(dst):
                     continue
                 if wv[1] is not None:
                     f.write('int %s(JKTask *t, int nsm, int smem_max, cudaStream_t s)\n'
-                            '{\n    if (t->nprim_p * t->nprim_q * t->nprim_r * t->nprim_s == 1)\n'
+                            '{\n    if (t->nprim_p * t->nprim_q * t->nprim_r * t->nprim_s == 1 && t->ratio2 == 0.)\n'
                             '        return jk_launch_warp<%d, %d, %d, %d, %d, %d, 1, 1>(t, nsm, smem_max, s);\n'
                             '    return jk_launch_warp<%d, %d, %d, %d, %d, %d, 0, 1>(t, nsm, smem_max, s);\n}\n'
                             % (name, lp, lq, lr, ls, wv[1], ndm, lp, lq, lr, ls, wv[0], ndm))
