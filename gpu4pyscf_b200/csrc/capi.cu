@@ -105,7 +105,9 @@ static int build_class_impl(double *vj, double *vk, const double *dm, int n_dm, 
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
-                        double omega, double scale, double ratio2 = 0., double omega2 = 0.)
+                        double omega, double scale, double ratio2 = 0., double omega2 = 0.,
+                        const float *sr_s_x = nullptr, const float4 *sr_g_x = nullptr,
+                        const float *sr_s_y = nullptr, const float4 *sr_g_y = nullptr, double sr_omega = 0.)
 {
     if (npair_x <= 0 || npair_y <= 0) return 0;
     if (RYS_b200_init()) return 1;
@@ -140,6 +142,11 @@ static int build_class_impl(double *vj, double *vk, const double *dm, int n_dm, 
     t.scale = scale;
     t.ratio2 = ratio2;
     t.omega2 = omega2;
+    if (sr_s_x != nullptr && sr_g_x != nullptr && sr_s_y != nullptr && sr_g_y != nullptr && vj == nullptr) {
+        // short-range exchange filter: K-only launches of the pure short-range operator
+        t.sr_s_x = sr_s_x; t.sr_g_x = sr_g_x; t.sr_s_y = sr_s_y; t.sr_g_y = sr_g_y;
+        t.sr_omega2 = (float)(sr_omega * sr_omega);
+    }
     t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
     t.rank = rank;
     t.world = world < 1 ? 1 : world;
@@ -184,7 +191,9 @@ static int build_rows_impl(double *vj, double *vk, double *vkT, const double *dm
                            const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
                            const float *dm_cond, float cutoff, float dm_penalty,
                            int dedupe, int rank, int world, unsigned long long *head, void *stream,
-                           double omega, double scale, double ratio2 = 0., double omega2 = 0.)
+                           double omega, double scale, double ratio2 = 0., double omega2 = 0.,
+                           const float *sr_s_x = nullptr, const float4 *sr_g_x = nullptr,
+                           const float *sr_s_y = nullptr, const float4 *sr_g_y = nullptr, double sr_omega = 0.)
 {
     if (npair_x <= 0 || nrows <= 0) return 0;
     if (RYS_b200_init()) return 1;
@@ -220,6 +229,10 @@ static int build_rows_impl(double *vj, double *vk, double *vkT, const double *dm
     t.scale = scale;
     t.ratio2 = ratio2;
     t.omega2 = omega2;
+    if (sr_s_x != nullptr && sr_g_x != nullptr && sr_s_y != nullptr && sr_g_y != nullptr && vj == nullptr) {
+        t.sr_s_x = sr_s_x; t.sr_g_x = sr_g_x; t.sr_s_y = sr_s_y; t.sr_g_y = sr_g_y;
+        t.sr_omega2 = (float)(sr_omega * sr_omega);
+    }
     t.rec_stride = pair_rec_stride(lprim[4] * lprim[5]);
     t.rank = rank;
     t.world = world < 1 ? 1 : world;
@@ -285,11 +298,14 @@ int B200_build_jk_rows(double *vj, double *vk, double *vkT, const double *dm, co
                        const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
                        const float *dm_cond, float cutoff, float dm_penalty,
                        int dedupe, int rank, int world, unsigned long long *head, void *stream,
-                       double omega, double scale, double ratio2, double omega2)
+                       double omega, double scale, double ratio2, double omega2,
+                       const float *sr_s_x, const void *sr_g_x, const float *sr_s_y, const void *sr_g_y,
+                       double sr_omega)
 {
     return build_rows_impl(vj, vk, vkT, dm, dmT, n_dm, nao, envs, lprim, pair_x, q_x, npair_x,
                            pair_y, q_y, rec_y, row_ptr, row_p, row_qmax, nrows,
-                           dm_cond, cutoff, dm_penalty, dedupe, rank, world, head, stream, omega, scale, ratio2, omega2);
+                           dm_cond, cutoff, dm_penalty, dedupe, rank, world, head, stream, omega, scale, ratio2, omega2,
+                           sr_s_x, (const float4 *)sr_g_x, sr_s_y, (const float4 *)sr_g_y, sr_omega);
 }
 
 int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int nao,
@@ -298,11 +314,14 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
-                        double omega, double scale, double ratio2, double omega2)
+                        double omega, double scale, double ratio2, double omega2,
+                        const float *sr_s_x, const void *sr_g_x, const float *sr_s_y, const void *sr_g_y,
+                        double sr_omega)
 {
     return build_class_impl(vj, vk, dm, n_dm, nao, envs, lprim, pair_x, q_x, npair_x, pair_y, q_y, npair_y,
                             dm_cond, cutoff, dm_penalty, q_margin, dedupe, rank, world, head, stream, rec_y,
-                            omega, scale, ratio2, omega2);
+                            omega, scale, ratio2, omega2,
+                            sr_s_x, (const float4 *)sr_g_x, sr_s_y, (const float4 *)sr_g_y, sr_omega);
 }
 
 // 1 if the kernel family serving the class evaluates two operator terms in one pass (thread-per-quartet
@@ -483,6 +502,28 @@ int int2e_qcond_estimator(float *q_out, RysIntEnvVars *envs, int shm_size,
     QB(4, 0); QB(4, 1); QB(4, 2); QB(4, 3); QB(4, 4);
 #undef QB
     return rt_last_error("qcond_batch_kernel");
+}
+
+// Reference signature (nr_sr_estimator.cu:400-414, called from scf/jk.py:1095-1105): short-range pair
+// estimator of every pair of the list.  B200_sr_pair_data is the native form that also returns the
+// (centre, exponent sum) record of each pair the quartet filter reads.
+int B200_sr_pair_data(float *s_estimator, void *geom, const RysIntEnvVars *envs, const uint32_t *bas_ij_idx,
+                      const float *diffuse_exps, const float *diffuse_ctr_coef, int npairs, double omega,
+                      void *stream)
+{
+    if (npairs <= 0) return 0;
+    const int nt = 128;
+    KLAUNCH(s_estimator_kernel, (npairs + nt - 1) / nt, nt, 0, (cudaStream_t)stream, s_estimator, (float4 *)geom,
+            bas_ij_idx, npairs, (const int *)envs->bas, (const double *)envs->env, envs->nbas,
+            diffuse_exps, diffuse_ctr_coef, (float)(omega < 0. ? -omega : omega));
+    return rt_last_error("s_estimator_kernel");
+}
+
+int fill_s_estimator(float *s_estimator, RysIntEnvVars *envs, uint32_t *bas_ij_idx, float *diffuse_exps,
+                     float *diffuse_ctr_coef, int npairs, double omega)
+{
+    return B200_sr_pair_data(s_estimator, nullptr, envs, bas_ij_idx, diffuse_exps, diffuse_ctr_coef, npairs,
+                             omega, nullptr);
 }
 
 // Overlap prescreen + enumeration of the shell pairs ish >= jsh, grouped by group pair

@@ -75,6 +75,14 @@ struct JKTask {
     // integral = scale * ( O[omega] + ratio2 * O[omega2] ),  ratio2 == 0: single term
     double ratio2;
     double omega2;
+    // short-range exchange filter (K-only launches of the pure short-range operator; reference:
+    // _fill_sr_vk_tasks, create_tasks.cu:245-369): per pair of the X / Y list the estimator s
+    // (fill_s_estimator) and (centre, exponent sum) of the most diffuse primitives; null = off
+    const float *sr_s_x;
+    const float *sr_s_y;
+    const float4 *sr_g_x;
+    const float4 *sr_g_y;
+    float sr_omega2;        // omega^2 of the attenuation
     const double *rec_y;    // optional per-pair records of the Y list (pair_record_kernel), or null
     int rec_stride;         // doubles per record
     int ychunk;             // work item = (X pair, chunk of `ychunk` consecutive Y candidates)
@@ -90,6 +98,18 @@ struct JKTask {
     const double *dmT;      // [n_dm, nao, nao] transposed density matrices (== dm when D is symmetric)
     double *vkT;            // [n_dm, nao, nao] receives the q-row K blocks transposed (== vk for symmetric D)
 };
+
+// Density threshold of the short-range filter for the quartet of pairs x and y: the largest exchange
+// density block must exceed it (and so must dm_penalty).  th_x = omega^2 a_x / (a_x + omega^2).
+// Same arithmetic as the reference (create_tasks.cu:343-352), FP32.
+__device__ __forceinline__ float sr_density_cutoff(const float4 gx, const float sx, const float th_x,
+                                                   const float4 gy, const float sy, const float cutoff)
+{
+    const float theta = th_x * gy.w / (th_x + gy.w);
+    const float dx = gx.x - gy.x, dy = gx.y - gy.y, dz = gx.z - gy.z;
+    const float rr = dx * dx + dy * dy + dz * dz;
+    return cutoff - sx - sy + logf(rr + 1.f) + theta * rr;
+}
 
 // Per-pair record (precomputed once per _VHFOpt.build, in pair-list order):
 //   [0..2] A-B, [3..5] A, [6] (int p0, int q0) AO offsets, [7] 0.5 if ish == jsh else 1,

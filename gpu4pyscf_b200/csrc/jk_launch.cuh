@@ -37,6 +37,9 @@ static inline int jk_set_chunks(JKTask *t, int workers)
     static const char *force = getenv("B200_YCHUNK");     // tests: exercise the chunk logic on tiny inputs
     if (force != nullptr && atoi(force) > 0) ch = atoi(force);
     else while (ch > 32 && (long long)t->npair_x * ((t->npair_y + ch - 1) / ch) < 8LL * workers * t->world) ch >>= 1;
+    // the flat kernels index work items with 32-bit integers (item = atomicAdd(head) * world + rank):
+    // grow the chunks until the item count stays far below 2^31 (pair lists of millions of entries)
+    while ((long long)t->npair_x * ((t->npair_y + ch - 1) / ch) > (1LL << 29)) ch <<= 1;
     t->ychunk = ch;
     t->nychunk = (t->npair_y + ch - 1) / ch;
     long long items = (long long)t->npair_x * t->nychunk;

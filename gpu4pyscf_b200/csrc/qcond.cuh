@@ -244,3 +244,52 @@ __global__ void pair_record_kernel(double *out, const uint32_t *pairs, int npair
             o[4] = ci[ip] * cj[jp] * exp(-ai * f * rr2);
         }
 }
+
+// Short-range pair estimator (reference: fill_s_estimator_kernel, nr_sr_estimator.cu:40-97, same FP32
+// formula): log of a bound on the short-range pair density built from the most diffuse primitives,
+// with the distance guess r_guess = 6 / sqrt(a_ij omega^2 / (omega^2 + a_ij)).  When `geom` is given it
+// also receives what the quartet filter needs per pair (create_tasks.cu:274-352): the centre of the
+// product of the two diffuse primitives and their exponent sum.
+__global__ void s_estimator_kernel(float *s_out, float4 *geom, const uint32_t *pairs, int npairs,
+                                   const int *bas, const double *env, int nbas,
+                                   const float *diffuse_exps, const float *diffuse_ctr_coef, float omega)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npairs) return;
+    const uint32_t pair = pairs[n];
+    const int ish = pair / nbas;
+    const int jsh = pair - ish * nbas;
+    const int li = bas[ish * BAS_SLOTS + ANG_OF];
+    const int lj = bas[jsh * BAS_SLOTS + ANG_OF];
+    const double *ri = env + bas[ish * BAS_SLOTS + PTR_BAS_COORD];
+    const double *rj = env + bas[jsh * BAS_SLOTS + PTR_BAS_COORD];
+    const float xi = (float)ri[0], yi = (float)ri[1], zi = (float)ri[2];
+    const float xjxi = (float)rj[0] - xi, yjyi = (float)rj[1] - yi, zjzi = (float)rj[2] - zi;
+    const float rr_ij = xjxi * xjxi + yjyi * yjyi + zjzi * zjzi;
+    const float ai = diffuse_exps[ish], aj = diffuse_exps[jsh];
+    const float aij = ai + aj;
+    const float aj_aij = aj / aij, ai_aij = ai / aij;
+    const float theta_ij = ai * aj / aij;
+    const float cicj = diffuse_ctr_coef[ish] * diffuse_ctr_coef[jsh];
+    const float omega2 = omega * omega;
+    const float fac_guess = .5f - logf(omega2) / 4;
+    const float omega_aij = omega2 / (omega2 + aij);
+    const float r_guess = 6.f / sqrtf(aij * omega_aij);
+    float norm = 1.f;
+    if (li >= 2) norm *= (2 * li + 1.f) / (4 * 3.14159265358979f);
+    if (lj >= 2) norm *= (2 * lj + 1.f) / (4 * 3.14159265358979f);
+    const float log_fac = logf(fabsf(cicj) * sqrtf(norm)) + 1.7171f - 1.5f * logf(aij) + fac_guess;
+    const float dri = aj_aij * r_guess, drj = ai_aij * r_guess;
+    const float dri_fac = .5f * li * logf(.5f * li / aij + dri * dri + 1e-9f);
+    const float drj_fac = .5f * lj * logf(.5f * lj / aij + drj * drj + 1e-9f);
+    const float est = dri_fac + drj_fac - theta_ij * rr_ij + log_fac;
+    s_out[n] = est > -700.f ? est : -700.f;
+    if (geom != nullptr) {
+        float4 g;
+        g.x = xi + xjxi * aj_aij;
+        g.y = yi + yjyi * aj_aij;
+        g.z = zi + zjzi * aj_aij;
+        g.w = aij;
+        geom[n] = g;
+    }
+}

@@ -124,6 +124,14 @@ rys_jk_rowt_kernel(JKTask t)
         const int rb = (int)(item / t.npair_x);
         const int ix = (int)(item - (long long)rb * t.npair_x);
         const float thr = t.cutoff - t.q_x[ix];
+        const bool sr = t.sr_s_x != nullptr;
+        float4 sr_gx = {0.f, 0.f, 0.f, 1.f};
+        float sr_sx = 0.f, sr_thx = 0.f;
+        if (sr) {
+            sr_gx = t.sr_g_x[ix];
+            sr_sx = t.sr_s_x[ix];
+            sr_thx = t.sr_omega2 * sr_gx.w / (sr_gx.w + t.sr_omega2);
+        }
         const int row_begin = rb * t.rows_per_item;
         const int row_end = min(t.nrows, row_begin + t.rows_per_item);
         // whole item dead?  (row_qmax is not sorted: test every row below, but skip the X setup when none survives)
@@ -239,6 +247,11 @@ rys_jk_rowt_kernel(JKTask t)
 #pragma unroll
                     for (int k = 0; k < JKR_SCREEN; ++k) {
                         bool keep = qy[k] + t.dm_penalty >= thr && dq[k] + qy[k] > thr;
+                        if (sr && keep) {
+                            const int y = ypos + k * 32 + lane;
+                            const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
+                            keep = t.dm_penalty > dc && dq[k] > dc;
+                        }
                         if (t.dedupe) {
                             const uint32_t canon = psh >= qsh[k] ? (uint32_t)psh * nbas + qsh[k]
                                                                  : (uint32_t)qsh[k] * nbas + psh;

@@ -245,6 +245,14 @@ rys_jk_thread_kernel(JKTask t)
         const int chunk = item / t.npair_x;
         const int ix = item - chunk * t.npair_x;
         const float thr = t.cutoff - t.q_x[ix];
+        const bool sr = t.sr_s_x != nullptr;
+        float4 sr_gx = {0.f, 0.f, 0.f, 1.f};
+        float sr_sx = 0.f, sr_thx = 0.f;
+        if (sr) {
+            sr_gx = t.sr_g_x[ix];
+            sr_sx = t.sr_s_x[ix];
+            sr_thx = t.sr_omega2 * sr_gx.w / (sr_gx.w + t.sr_omega2);
+        }
         int ypos = chunk * t.ychunk;
         if (t.dedupe == 1 && ypos < ix) ypos = ix;
         const int y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
@@ -328,6 +336,10 @@ rys_jk_thread_kernel(JKTask t)
                                 dmax = fmaxf(dmax, fmaxf(dc_s[psh], dc_s[qsh]));
                             }
                             keep = dmax + qy > thr;
+                            if (sr && keep) {
+                                const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
+                                keep = t.dm_penalty > dc && dmax > dc;
+                            }
                         }
                     }
                 }

@@ -362,6 +362,14 @@ rys_jk_warp_kernel(JKTask t)
             y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
         }
         const float thr = t.cutoff - t.q_x[ix];
+        const bool sr = t.sr_s_x != nullptr;
+        float4 sr_gx = {0.f, 0.f, 0.f, 1.f};
+        float sr_sx = 0.f, sr_thx = 0.f;
+        if (sr) {
+            sr_gx = t.sr_g_x[ix];
+            sr_sx = t.sr_s_x[ix];
+            sr_thx = t.sr_omega2 * sr_gx.w / (sr_gx.w + t.sr_omega2);
+        }
         if (ROW) {
             bool any_row = false;
             for (int row = row_begin + lt; row < row_end; row += TEAM)
@@ -500,6 +508,10 @@ rys_jk_warp_kernel(JKTask t)
                         if (do_j) dmax = fmaxf(dmax, dc_prow[qsh]);
                         if (do_k) dmax = fmaxf(dmax, fmaxf(dc_r[qsh], dc_s[qsh]));
                         keep = keep && (dmax + qy > thr);
+                        if (sr && keep) {
+                            const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
+                            keep = t.dm_penalty > dc && dmax > dc;
+                        }
                     }
                 } else {
                     float qy = t.q_y[y];
@@ -521,6 +533,10 @@ rys_jk_warp_kernel(JKTask t)
                                 dmax = fmaxf(dmax, fmaxf(dc_s[psh], dc_s[qsh]));
                             }
                             keep = dmax + qy > thr;
+                            if (sr && keep) {
+                                const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
+                                keep = t.dm_penalty > dc && dmax > dc;
+                            }
                         }
                     }
                 }

@@ -51,14 +51,18 @@ def load_library(name='libgvhf_rys_b200'):
         vp, vp, vp, c_int, c_int, vp, vp,
         vp, vp, c_int, vp, vp, c_int,
         vp, c_float, c_float, c_float, c_int, c_int, c_int, vp, vp, vp,
-        ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+        ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, ctypes.c_double]
     lib.B200_build_jk_rows.restype = c_int
     lib.B200_build_jk_rows.argtypes = [
         vp, vp, vp, vp, vp, c_int, c_int, vp, vp,
         vp, vp, c_int,
         vp, vp, vp, vp, vp, vp, c_int,
         vp, c_float, c_float, c_int, c_int, c_int, vp, vp,
-        ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+        ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, ctypes.c_double]
+    lib.B200_sr_pair_data.restype = c_int
+    lib.B200_sr_pair_data.argtypes = [vp, vp, vp, vp, vp, vp, c_int, ctypes.c_double, vp]
+    lib.fill_s_estimator.restype = c_int
+    lib.fill_s_estimator.argtypes = [vp, vp, vp, vp, vp, c_int, ctypes.c_double]
     lib.B200_class_two_terms.restype = c_int
     lib.B200_class_two_terms.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.B200_class_kind.restype = c_int

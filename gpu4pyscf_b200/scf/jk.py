@@ -177,6 +177,7 @@ class _PairLists:
         self.tasks = None
         self.qmax = None
         self.launch_cost = None
+        self.sr = None            # short-range filter data: {'omega': w, 'flat': {key: (s, geom)}}
 
 
 def _estimator_operator(terms):
@@ -213,6 +214,7 @@ class _VHFOpt:
         self._lists = {}
         self._cur = _PairLists()
         self._default = None
+        self._diffuse_dev = None
         # multi-GPU partition (set by the caller or picked up from torch.distributed)
         self.rank = None
         self.world = None
@@ -243,6 +245,7 @@ class _VHFOpt:
         self._lists = {}
         self._cur = _PairLists()
         self._default = None
+        self._diffuse_dev = None
         return self
 
     def _use_lists(self, terms):
@@ -257,9 +260,29 @@ class _VHFOpt:
             pl.cache = _cache_q_cond_and_non0pairs(
                 self.sorted_mol, self._rys_envs, self.direct_scf_tol, self.device, lib, self.q_bin,
                 _estimator_operator(key))
+            if len(key) == 2 and key[0][1] == 0 and key[1][0] == -key[0][0]:
+                # pure short-range operator c * erfc(w r)/r: pair estimators for the quartet filter
+                # (reference: fill_s_estimator under omega < 0, scf/jk.py:1089-1105)
+                w = key[1][1]
+                pl.sr = {'omega': w, 'flat': {k: self._sr_pair_data(v[0], w) for k, v in pl.cache.items()}}
             self._lists[key] = pl
         self._cur = pl
         return pl
+
+    def _sr_pair_data(self, ids, omega):
+        '''(s, geom) of a pair list for the short-range quartet filter (B200_sr_pair_data)'''
+        lib = loader.load_library()
+        if getattr(self, '_diffuse_dev', None) is None:
+            exps, cs = _diffuse_pgto_params(self.sorted_mol)
+            self._diffuse_dev = (torch.as_tensor(exps, device=self.device), torch.as_tensor(cs, device=self.device))
+        n = len(ids)
+        s_est = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+        geom = torch.empty((max(n, 1), 4), dtype=torch.float32, device=self.device)
+        if n and lib.B200_sr_pair_data(_ptr(s_est), _ptr(geom), ctypes.byref(self._rys_envs), _ptr(ids),
+                                       _ptr(self._diffuse_dev[0]), _ptr(self._diffuse_dev[1]), n, float(omega),
+                                       loader.current_stream_ptr()):
+            raise RuntimeError('B200_sr_pair_data failed')
+        return s_est, geom
 
     # ------------------------------------------------------------------
     def build(self, group_size=None, verbose=None):
@@ -352,7 +375,10 @@ class _VHFOpt:
                                         loader.current_stream_ptr())
             if err:
                 raise RuntimeError('B200_pair_records failed')
-        out = dict(pair=pair, q=qv, rec=rec, row_ptr=row_ptr, row_p=row_p, row_qmax=row_qmax,
+        sr_s = sr_g = None
+        if self._cur.sr is not None:
+            sr_s, sr_g = self._sr_pair_data(pair, self._cur.sr['omega'])
+        out = dict(pair=pair, q=qv, rec=rec, row_ptr=row_ptr, row_p=row_p, row_qmax=row_qmax, sr_s=sr_s, sr_g=sr_g,
                    nrows=len(row_p), mean_len=len(pair) / max(1, len(row_p)),
                    lp=int(uniq[gp, 0]), lq=int(uniq[gq, 0]), nprim_p=npp, nprim_q=npq)
         self._rows[key] = out
@@ -568,6 +594,11 @@ class _VHFOpt:
                 ops = [(terms[0][1], terms[0][0], terms[1][0] / terms[0][0], terms[1][1])]
             else:
                 ops = [(w, c, 0., 0.) for c, w in terms]
+            # short-range exchange filter: K-only builds of the pure short-range operator
+            srd = self._cur.sr if (not with_j and os.environ.get('B200_SR_FILTER', '1') == '1') else None
+            sr_x = srd['flat'][kx] if srd else (None, None)
+            sr_y = ((rl['sr_s'], rl['sr_g']) if mode == 'row' else srd['flat'][ky]) if srd else (None, None)
+            sr_w = float(srd['omega']) if srd else 0.
             for iop, (op_w, op_scale, op_ratio2, op_w2) in enumerate(ops):
                 head = ctypes.c_void_p(heads.data_ptr() + 8 * (2 * it + iop))
                 if mode == 'row':
@@ -577,7 +608,8 @@ class _VHFOpt:
                         _ptr(rl['pair']), _ptr(rl['q']), _ptr(rl['rec']),
                         _ptr(rl['row_ptr']), _ptr(rl['row_p']), _ptr(rl['row_qmax']), rl['nrows'],
                         _ptr(dm_cond), cutoff, dm_penalty, dedupe, l_rank, l_world, head, stream,
-                        float(op_w), float(op_scale), float(op_ratio2), float(op_w2))
+                        float(op_w), float(op_scale), float(op_ratio2), float(op_w2),
+                        _ptr(sr_x[0]), _ptr(sr_x[1]), _ptr(sr_y[0]), _ptr(sr_y[1]), sr_w)
                 else:
                     pair_y, q_y = self._cur.cache[ky][:2]
                     rec_y = self._cur.cache[ky][3]
@@ -585,7 +617,8 @@ class _VHFOpt:
                         _ptr(vj), _ptr(vk), _ptr(dms), ndm_k, nao, ctypes.byref(envs), lprim,
                         _ptr(pair_x), _ptr(q_x), len(pair_x), _ptr(pair_y), _ptr(q_y), len(pair_y),
                         _ptr(dm_cond), cutoff, dm_penalty, float(self.q_bin), dedupe, l_rank, l_world, head, stream,
-                        _ptr(rec_y), float(op_w), float(op_scale), float(op_ratio2), float(op_w2))
+                        _ptr(rec_y), float(op_w), float(op_scale), float(op_ratio2), float(op_w2),
+                        _ptr(sr_x[0]), _ptr(sr_x[1]), _ptr(sr_y[0]), _ptr(sr_y[1]), sr_w)
                 if err:
                     break
             if err:

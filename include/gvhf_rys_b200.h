@@ -103,7 +103,9 @@ int B200_build_jk_class(double *vj, double *vk, const double *dm, int n_dm, int 
                         const uint32_t *pair_y, const float *q_y, int npair_y,
                         const float *dm_cond, float cutoff, float dm_penalty, float q_margin,
                         int dedupe, int rank, int world, int *head, void *stream, const double *rec_y,
-                        double omega, double scale, double ratio2, double omega2);
+                        double omega, double scale, double ratio2, double omega2,
+                        const float *sr_s_x, const void *sr_g_x, const float *sr_s_y, const void *sr_g_y,
+                        double sr_omega);
 
 /* Native entry, row-stream kernels (csrc/rys_jk_rowt.cuh, ROW variant of rys_jk_warp.cuh): one
  * angular class with the streamed list grouped in ROWS of one shell p.
@@ -125,7 +127,21 @@ int B200_build_jk_rows(double *vj, double *vk, double *vkT, const double *dm, co
                        const int *row_ptr, const int *row_p, const float *row_qmax, int nrows,
                        const float *dm_cond, float cutoff, float dm_penalty,
                        int dedupe, int rank, int world, unsigned long long *head, void *stream,
-                       double omega, double scale, double ratio2, double omega2);
+                       double omega, double scale, double ratio2, double omega2,
+                       const float *sr_s_x, const void *sr_g_x, const float *sr_s_y, const void *sr_g_y,
+                        double sr_omega);
+
+/* Short-range exchange filter of the native launches (sr_* arguments, sr_omega = |omega|; all NULL = off; only honoured by K-only
+ * launches): per pair of the X / Y list the estimator s and a float4 (centre, exponent sum) record, both
+ * from B200_sr_pair_data.  A quartet is kept only if dm_penalty and its largest exchange density bound
+ * exceed  cutoff - s_x - s_y + log(R^2 + 1) + theta R^2  -- the reference's _fill_sr_vk_tasks
+ * (create_tasks.cu:245-369), applied, like there, to the pure short-range operator (lr_factor == 0).
+ * fill_s_estimator: reference signature (nr_sr_estimator.cu:400-414, scf/jk.py:1095-1105), the estimator only. */
+int B200_sr_pair_data(float *s_estimator, void *geom, const RysIntEnvVars *envs, const uint32_t *bas_ij_idx,
+                      const float *diffuse_exps, const float *diffuse_ctr_coef, int npairs, double omega,
+                      void *stream);
+int fill_s_estimator(float *s_estimator, RysIntEnvVars *envs, uint32_t *bas_ij_idx, float *diffuse_exps,
+                     float *diffuse_ctr_coef, int npairs, double omega);
 
 /* Operator of a native launch: every integral is  scale * ( O[omega] + ratio2 * O[omega2] )  with O[0] = 1/r and
  * O[w > 0] = erf(w r)/r; ratio2 = 0 is a single term.  The short-range operator erfc(w r)/r is (omega = 0,

@@ -33,6 +33,7 @@ struct dim3 {
 };
 struct uint3_ { unsigned x, y, z; };
 struct double2 { double x, y; };
+struct float4 { float x, y, z, w; };
 
 extern uint3_ threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
