@@ -120,6 +120,25 @@ for om, lrf, srf in ((0., 1., 1.), (0.4, 1., 0.), (-0.4, 0., 1.)):
     ref = np.log(oracle.q_cond(smol, omega=om)[idn // nbas, idn %% nbas])
     assert abs(q.numpy() - ref).max() < 2e-5, (om, abs(q.numpy() - ref).max())
 
+# fill_s_estimator (reference signature, nr_sr_estimator.cu:400-414) against a numpy restatement of the formula
+from gpu4pyscf_b200.scf.jk import _diffuse_pgto_params
+ex, cs = _diffuse_pgto_params(smol)
+s_out = torch.empty(len(ids), dtype=torch.float32)
+assert lib.fill_s_estimator(jk._ptr(s_out), ctypes.byref(opt.rys_envs), jk._ptr(ids), jk._ptr(torch.as_tensor(ex)),
+                            jk._ptr(torch.as_tensor(cs)), len(ids), -0.4) == 0
+ish, jsh = idn // nbas, idn %% nbas
+R = np.array([smol._env[b[7]:b[7] + 3] for b in smol._bas])
+ll = smol._bas[:, 1].astype(float)
+ai, aj = ex[ish].astype(float), ex[jsh].astype(float)
+aij = ai + aj
+rr = ((R[ish] - R[jsh]) ** 2).sum(axis=1)
+rg = 6. / np.sqrt(aij * 0.16 / (0.16 + aij))
+norm = np.where(ll[ish] >= 2, (2 * ll[ish] + 1) / (4 * np.pi), 1.) * np.where(ll[jsh] >= 2, (2 * ll[jsh] + 1) / (4 * np.pi), 1.)
+ref_s = (.5 * ll[ish] * np.log(.5 * ll[ish] / aij + (aj / aij * rg) ** 2 + 1e-9)
+         + .5 * ll[jsh] * np.log(.5 * ll[jsh] / aij + (ai / aij * rg) ** 2 + 1e-9)
+         - ai * aj / aij * rr + np.log(cs[ish] * cs[jsh] * np.sqrt(norm)) + 1.7171 - 1.5 * np.log(aij) + .5 - np.log(0.16) / 4)
+assert abs(s_out.numpy() - ref_s).max() < 2e-4, abs(s_out.numpy() - ref_s).max()
+
 # pair prescreen: the group-pair lists hold exactly the ish >= jsh pairs of their two groups, once each
 seen = set()
 grp = np.repeat(np.arange(ng), smol.l_ctr_counts)
