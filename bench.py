@@ -14,11 +14,16 @@ partials when N > 1 and the symmetrisation.
   e2e     : s/build through the public plugin call `scf.jk.get_jk(mol, dm_host)`
             with the density in pinned host memory and J, K read back to the host
             inside the timed region
-  roofline: FP64-FMA bound.  achieved = F_alg / t (F_alg: SURVEY.md 8d flop model
-            x surviving quartets counted by the kernels); peak = DFMA burn
-            measured in this very run (B200_dfma_burn)
+  roofline: FP64-FMA bound.  achieved = min(F_alg, F_hw) / t with F_alg = SURVEY.md 8d
+            flop model x surviving quartets counted by the kernels in this run and
+            F_hw = 2*DFMA + DMUL + DADD thread instructions of one build from the
+            committed ncu capture (profiles/ncu_r2/build_counters_*.json, which also
+            supplies the measured DRAM traffic); peak = DFMA burn measured in this
+            very run (B200_dfma_burn); frac_of_nominal is against 37.2 TFLOP/s
   cpu_baseline: the CPU oracle (oracle/md_jk.c, OpenMP) timed on a fragment of
-            the same molecule and scaled by algorithmic flops
+            the same molecule and scaled by algorithmic flops, plus the measured
+            full-molecule oracle runs of the golden fixtures with the GPU time of
+            the same build beside them
 
 `--impl reference` times only the CPU oracle (PySCF/libcvhf cannot be installed
 here: see DESIGN.md), on the same bounded sample.

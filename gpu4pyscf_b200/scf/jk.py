@@ -13,9 +13,12 @@ grouped by one shell of the pair (the streamed Y side of the row-stream kernels:
 three shells of every quartet a warp evaluates are warp-uniform).  One launch
 handles an unordered pair of group pairs; which of the two is streamed, and
 through which kernel family, is decided per launch (``class_tasks``).
-Multi-GPU: one process per GPU; every rank takes the work items with
-``item % world == rank`` of each launch and the partial ``[vj|vk]`` buffer is
-summed with ONE ``all_reduce`` per build.
+Screening lists exist per OPERATOR (``_VHFOpt._use_lists``): 1/r, erf(w r)/r, or a sum
+of both evaluated in one pass (range-separated exchange), each with its own Schwarz
+bounds; pure short-range K builds add the distance-dependent quartet filter.
+Multi-GPU: one process per GPU; the work items of the heavy launches are dealt
+``item % world == rank``, light launches run whole on one rank (assigned by measured
+cost), and the partial ``[vj|vk]`` buffer is summed with ONE ``all_reduce`` per build.
 """
 import ctypes
 import math

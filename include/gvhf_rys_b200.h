@@ -89,8 +89,8 @@ int RYS_build_k(double *vk, double *dm, int n_dm, int nao, double omega, double 
  *   dedupe 0: all X x Y quartets; 1: X and Y are the same list, keep iy >= ix;
  *          2/3: keep pair_x >= pair_y / pair_y >= pair_x (reference semantics).
  *   q_margin: 0 for exactly sorted q_y, 4 for the reference's binned order.
- *   rank/world: X pairs ix with ix % world == rank are processed (multi-GPU
- *   partition of the q-sorted list); head: zeroed device int work counter.
+ *   rank/world: the work items (X pair, chunk of the Y list) with item % world == rank are
+ *   processed (multi-GPU partition); head: zeroed device int work counter.
  *   rec_y: optional per-pair records of the Y list (B200_pair_records), NULL to
  *   derive the Gaussian products from bas/env inside the kernel.
  *   omega, scale, ratio2, omega2: the operator, see B200_class_two_terms below (omega = 0 for 1/r, > 0
