@@ -111,6 +111,22 @@ __device__ __forceinline__ float sr_density_cutoff(const float4 gx, const float 
     return cutoff - sx - sy + logf(rr + 1.f) + theta * rr;
 }
 
+// The filter for candidate y of the Y list against X pair ix; everything is read here (L1/L2 hits, only
+// in short-range builds) so that the kernels keep no filter state in registers on their common path.
+// (The task fields are passed by value: taking the address of a kernel parameter would copy the whole
+// struct to local memory.)
+static __device__ __forceinline__ bool sr_keep_(const float4 *g_x, const float *s_x, const float4 *g_y, const float *s_y,
+                                             const float omega2, const float cutoff, const float dm_penalty,
+                                             const int ix, const int y, const float dmax)
+{
+    const float4 gx = g_x[ix];
+    const float th_x = omega2 * gx.w / (gx.w + omega2);
+    const float dc = sr_density_cutoff(gx, s_x[ix], th_x, g_y[y], s_y[y], cutoff);
+    return dm_penalty > dc && dmax > dc;
+}
+#define sr_keep(t, ix, y, dmax) \
+    sr_keep_((t).sr_g_x, (t).sr_s_x, (t).sr_g_y, (t).sr_s_y, (t).sr_omega2, (t).cutoff, (t).dm_penalty, ix, y, dmax)
+
 // Per-pair record (precomputed once per _VHFOpt.build, in pair-list order):
 //   [0..2] A-B, [3..5] A, [6] (int p0, int q0) AO offsets, [7] 0.5 if ish == jsh else 1,
 //   then per primitive pair: zeta, Px, Py, Pz, ci*cj*exp(-ai*aj/zeta*|AB|^2)

@@ -168,6 +168,19 @@ int jk_launch_warp(JKTask *t, int nsm, int smem_max, cudaStream_t stream)
     const int budget = (smem_max + 1024) / minb - 1024;
     while (!ROW && K > 1 && smem_of(K) > budget) --K;
     while (nteams > 1 && smem_of(K) > smem_max) --nteams;     // fewer teams per block for the fattest classes
+    // mid-size tiles: one 384-thread block per SM when shared memory keeps the 128-thread blocks below the
+    // 12 warps the registers allow (B200_BIG_BLOCKS=0 disables)
+    {
+        static const char *big = getenv("B200_BIG_BLOCKS");
+        const int nt_big = jkw_bound_threads(C::TEAM, C::TILE * (1 + NDM), ROW);
+        if ((big == nullptr || big[0] != '0') && nt_big > nteams * C::TEAM && smem_of(K) <= smem_max) {
+            const int per_sm_small = rt_prepare(rys_jk_warp_kernel<LP, LQ, LR, LS, NCS, NDM, BL, ROW>, smem_of(K),
+                                                nteams * C::TEAM);
+            const int small_teams = nteams;
+            nteams = nt_big / C::TEAM;
+            if (smem_of(K) > smem_max || per_sm_small * small_teams >= nteams) nteams = small_teams;
+        }
+    }
     const int nt = nteams * C::TEAM;
     int smem = smem_of(K);
     if (smem > smem_max) {

@@ -235,12 +235,7 @@ rys_jk_kernel(JKTask t)
                                 dmax = fmaxf(dmax, fmaxf(dc_s[psh], dc_s[qsh]));
                             }
                             keep = dmax + qy > thr;
-                            if (t.sr_s_x != nullptr && keep) {     // short-range exchange filter (common.cuh)
-                                const float4 gx = t.sr_g_x[ix];
-                                const float thx = t.sr_omega2 * gx.w / (gx.w + t.sr_omega2);
-                                const float dc = sr_density_cutoff(gx, t.sr_s_x[ix], thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
-                                keep = t.dm_penalty > dc && dmax > dc;
-                            }
+                            if (t.sr_s_x != nullptr && keep) keep = sr_keep(t, ix, y, dmax);     // common.cuh
                         }
                     }
                 }

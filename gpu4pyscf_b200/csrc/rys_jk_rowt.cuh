@@ -91,6 +91,7 @@ rys_jk_rowt_kernel(JKTask t)
     const int tid = threadIdx.x;
     const int npq = t.nprim_p * t.nprim_q;
     const int nrs = t.nprim_r * t.nprim_s;
+    const int nterm = t.ratio2 != 0. ? 2 : 1;
     const int nbas = t.nbas;
     const int nao = t.nao;
     const size_t nao2 = (size_t)nao * nao;
@@ -124,14 +125,6 @@ rys_jk_rowt_kernel(JKTask t)
         const int rb = (int)(item / t.npair_x);
         const int ix = (int)(item - (long long)rb * t.npair_x);
         const float thr = t.cutoff - t.q_x[ix];
-        const bool sr = t.sr_s_x != nullptr;
-        float4 sr_gx = {0.f, 0.f, 0.f, 1.f};
-        float sr_sx = 0.f, sr_thx = 0.f;
-        if (sr) {
-            sr_gx = t.sr_g_x[ix];
-            sr_sx = t.sr_s_x[ix];
-            sr_thx = t.sr_omega2 * sr_gx.w / (sr_gx.w + t.sr_omega2);
-        }
         const int row_begin = rb * t.rows_per_item;
         const int row_end = min(t.nrows, row_begin + t.rows_per_item);
         // whole item dead?  (row_qmax is not sorted: test every row below, but skip the X setup when none survives)
@@ -247,11 +240,7 @@ rys_jk_rowt_kernel(JKTask t)
 #pragma unroll
                     for (int k = 0; k < JKR_SCREEN; ++k) {
                         bool keep = qy[k] + t.dm_penalty >= thr && dq[k] + qy[k] > thr;
-                        if (sr && keep) {
-                            const int y = ypos + k * 32 + lane;
-                            const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
-                            keep = t.dm_penalty > dc && dq[k] > dc;
-                        }
+                        if (t.sr_s_x != nullptr && keep) keep = sr_keep(t, ix, ypos + k * 32 + lane, dq[k]);
                         if (t.dedupe) {
                             const uint32_t canon = psh >= qsh[k] ? (uint32_t)psh * nbas + qsh[k]
                                                                  : (uint32_t)qsh[k] * nbas + psh;
@@ -292,14 +281,13 @@ rys_jk_rowt_kernel(JKTask t)
                         const double *pr = rec + PAIR_REC_HDR + ipq * 5;
                         const double zeta = pr[0], Px = pr[1], Py = pr[2], Pz = pr[3];
                         const double cpq = fac * pr[4];
-                        for (int irs = 0; irs < nrs; ++irs) {
-                            jkt_prim_quartet<LP, LQ, LR, LS>(gout, zeta, Px, Py, Pz, cpq, Ax, Ay, Az, ABx, ABy, ABz,
+                        for (int it = 0; it < nrs * nterm; ++it) {       // operator terms: one call site
+                            const int term = it / nrs;
+                            const int irs = it - term * nrs;
+                            jkt_prim_quartet<LP, LQ, LR, LS>(gout, zeta, Px, Py, Pz, term ? cpq * t.ratio2 : cpq,
+                                                             Ax, Ay, Az, ABx, ABy, ABz,
                                                              rsprim + irs * 5, Cx, Cy, Cz, CDx, CDy, CDz,
-                                                             t.omega, rys_tab);
-                            if (t.ratio2 != 0.)      // second operator term into the same integrals
-                                jkt_prim_quartet<LP, LQ, LR, LS>(gout, zeta, Px, Py, Pz, cpq * t.ratio2, Ax, Ay, Az,
-                                                                 ABx, ABy, ABz, rsprim + irs * 5, Cx, Cy, Cz,
-                                                                 CDx, CDy, CDz, t.omega2, rys_tab);
+                                                             term ? t.omega2 : t.omega, rys_tab);
                         }
                     }
 

@@ -213,6 +213,7 @@ rys_jk_thread_kernel(JKTask t)
     const int NT = blockDim.x;
     const int npq = t.nprim_p * t.nprim_q;
     const int nrs = t.nprim_r * t.nprim_s;
+    const int nterm = t.ratio2 != 0. ? 2 : 1;
     const int nbas = t.nbas;
     const int nao = t.nao;
     const size_t nao2 = (size_t)nao * nao;
@@ -245,14 +246,6 @@ rys_jk_thread_kernel(JKTask t)
         const int chunk = item / t.npair_x;
         const int ix = item - chunk * t.npair_x;
         const float thr = t.cutoff - t.q_x[ix];
-        const bool sr = t.sr_s_x != nullptr;
-        float4 sr_gx = {0.f, 0.f, 0.f, 1.f};
-        float sr_sx = 0.f, sr_thx = 0.f;
-        if (sr) {
-            sr_gx = t.sr_g_x[ix];
-            sr_sx = t.sr_s_x[ix];
-            sr_thx = t.sr_omega2 * sr_gx.w / (sr_gx.w + t.sr_omega2);
-        }
         int ypos = chunk * t.ychunk;
         if (t.dedupe == 1 && ypos < ix) ypos = ix;
         const int y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
@@ -336,10 +329,9 @@ rys_jk_thread_kernel(JKTask t)
                                 dmax = fmaxf(dmax, fmaxf(dc_s[psh], dc_s[qsh]));
                             }
                             keep = dmax + qy > thr;
-                            if (sr && keep) {
-                                const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
-                                keep = t.dm_penalty > dc && dmax > dc;
-                            }
+                            // short-range exchange filter; the X-pair data are re-read there so that the
+                            // common path carries no extra live registers
+                            if (t.sr_s_x != nullptr && keep) keep = sr_keep(t, ix, y, dmax);
                         }
                     }
                 }
@@ -426,14 +418,15 @@ rys_jk_thread_kernel(JKTask t)
                         Px = Ax - fq * ABx; Py = Ay - fq * ABy; Pz = Az - fq * ABz;
                         cpq = fac * cp[ip] * cq[iq] * exp(-ap * fq * rr2);
                     }
-                    for (int irs = 0; irs < nrs; ++irs) {
-                        jkt_prim_quartet<LP, LQ, LR, LS, NCP>(gout, zeta, Px, Py, Pz, cpq, Ax, Ay, Az, ABx, ABy, ABz,
+                    // operator terms (JKTask::ratio2) share ONE call site: measured in registers and stack, this
+                    // form costs the single-term path nothing (a second inlined call or a per-term table did)
+                    for (int it = 0; it < nrs * nterm; ++it) {
+                        const int term = it / nrs;
+                        const int irs = it - term * nrs;
+                        jkt_prim_quartet<LP, LQ, LR, LS, NCP>(gout, zeta, Px, Py, Pz, term ? cpq * t.ratio2 : cpq,
+                                                              Ax, Ay, Az, ABx, ABy, ABz,
                                                               rsprim + irs * 5, Cx, Cy, Cz, CDx, CDy, CDz,
-                                                              t.omega, rys_tab, c_lo);
-                        if (t.ratio2 != 0.)      // second operator term into the same integrals
-                            jkt_prim_quartet<LP, LQ, LR, LS, NCP>(gout, zeta, Px, Py, Pz, cpq * t.ratio2, Ax, Ay, Az,
-                                                                  ABx, ABy, ABz, rsprim + irs * 5, Cx, Cy, Cz,
-                                                                  CDx, CDy, CDz, t.omega2, rys_tab, c_lo);
+                                                              term ? t.omega2 : t.omega, rys_tab, c_lo);
                     }
                 }
 

@@ -219,6 +219,21 @@ __host__ __device__ constexpr int jkw_block_threads(int team, int d)
 {
     return team > jkw_max_threads(d) ? team : (jkw_max_threads(d) / team) * team;
 }
+// Launch bounds.  The mid-size tiles (170 registers) may also run as ONE block of 384 threads per SM
+// instead of three blocks of 128: same register budget, but the Rys table slice is staged once per SM,
+// which lets 12 warps fit where shared memory admits only two 128-thread blocks (the launcher decides).
+// Only for the single-warp-team row-stream kernels: elsewhere the 384-thread bound made ptxas spill
+// more at the same register count ((21|33) rows: 160 -> 248 B of stack) and no launch needed it.
+__host__ __device__ constexpr bool jkw_big_ok(int team, int d, int row) { return row && team == 32 && d > 24 && d <= 44; }
+__host__ __device__ constexpr int jkw_bound_threads(int team, int d, int row)
+{
+    return jkw_big_ok(team, d, row) ? 384 : jkw_block_threads(team, d);
+}
+__host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int team);
+__host__ __device__ constexpr int jkw_bound_blocks(int tile, int ndm, int sub, int team, int row)
+{
+    return jkw_big_ok(team, tile * (1 + ndm), row) ? 1 : jkw_minblocks(tile, ndm, sub, team);
+}
 __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int team)
 {
     int d = tile * (1 + ndm);
@@ -236,11 +251,11 @@ __host__ __device__ constexpr int jkw_minblocks(int tile, int ndm, int sub, int 
 // the q-dependent blocks are addressed with q as the column index (dmT / vkT), see rys_jk_rowt.cuh.
 template <int LP, int LQ, int LR, int LS, int NCS, int NDM, int BL = 0, int ROW = 0>
 __global__ void
-__launch_bounds__(jkw_block_threads(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM,
-                                    JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE * (1 + NDM)),
-                  jkw_minblocks(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE, NDM,
+__launch_bounds__(jkw_bound_threads(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM,
+                                    JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE * (1 + NDM), ROW),
+                  jkw_bound_blocks(JKWCfg<LP, LQ, LR, LS, NCS, BL>::TILE, NDM,
                                 NCS == 1 ? JKWCfg<LP, LQ, LR, LS, NCS, BL>::SUBSIZE : LS + 1,
-                                JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM))
+                                JKWCfg<LP, LQ, LR, LS, NCS, BL>::TEAM, ROW))
 rys_jk_warp_kernel(JKTask t)
 {
     typedef JKWCfg<LP, LQ, LR, LS, NCS, BL> C;
@@ -362,14 +377,6 @@ rys_jk_warp_kernel(JKTask t)
             y_end = min(t.npair_y, (chunk + 1) * t.ychunk);
         }
         const float thr = t.cutoff - t.q_x[ix];
-        const bool sr = t.sr_s_x != nullptr;
-        float4 sr_gx = {0.f, 0.f, 0.f, 1.f};
-        float sr_sx = 0.f, sr_thx = 0.f;
-        if (sr) {
-            sr_gx = t.sr_g_x[ix];
-            sr_sx = t.sr_s_x[ix];
-            sr_thx = t.sr_omega2 * sr_gx.w / (sr_gx.w + t.sr_omega2);
-        }
         if (ROW) {
             bool any_row = false;
             for (int row = row_begin + lt; row < row_end; row += TEAM)
@@ -508,10 +515,7 @@ rys_jk_warp_kernel(JKTask t)
                         if (do_j) dmax = fmaxf(dmax, dc_prow[qsh]);
                         if (do_k) dmax = fmaxf(dmax, fmaxf(dc_r[qsh], dc_s[qsh]));
                         keep = keep && (dmax + qy > thr);
-                        if (sr && keep) {
-                            const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
-                            keep = t.dm_penalty > dc && dmax > dc;
-                        }
+                        if (t.sr_s_x != nullptr && keep) keep = sr_keep(t, ix, y, dmax);
                     }
                 } else {
                     float qy = t.q_y[y];
@@ -533,10 +537,7 @@ rys_jk_warp_kernel(JKTask t)
                                 dmax = fmaxf(dmax, fmaxf(dc_s[psh], dc_s[qsh]));
                             }
                             keep = dmax + qy > thr;
-                            if (sr && keep) {
-                                const float dc = sr_density_cutoff(sr_gx, sr_sx, sr_thx, t.sr_g_y[y], t.sr_s_y[y], t.cutoff);
-                                keep = t.dm_penalty > dc && dmax > dc;
-                            }
+                            if (t.sr_s_x != nullptr && keep) keep = sr_keep(t, ix, y, dmax);
                         }
                     }
                 }
