@@ -114,8 +114,9 @@ __device__ __forceinline__ float sr_density_cutoff(const float4 gx, const float 
 // The filter for candidate y of the Y list against X pair ix; everything is read here (L1/L2 hits, only
 // in short-range builds) so that the kernels keep no filter state in registers on their common path.
 // (The task fields are passed by value: taking the address of a kernel parameter would copy the whole
-// struct to local memory.)
-static __device__ __forceinline__ bool sr_keep_(const float4 *g_x, const float *s_x, const float4 *g_y, const float *s_y,
+// struct to local memory.  Not inlined on purpose: the registers the call clobbers are saved inside the
+// short-range branch only, so builds without the filter execute no extra spill code.)
+static __device__ __noinline__ bool sr_keep_(const float4 *g_x, const float *s_x, const float4 *g_y, const float *s_y,
                                              const float omega2, const float cutoff, const float dm_penalty,
                                              const int ix, const int y, const float dmax)
 {
