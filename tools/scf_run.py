@@ -38,7 +38,7 @@ def timed_veff(*a, **k):
     out = orig(*a, **k)
     e1.record(); e1.synchronize()
     veff_ms.append(e0.elapsed_time(e1))
-    print('  get_veff %d: %.0f ms (J and K passes, %s density)' % (len(veff_ms), veff_ms[-1],
+    print('  get_veff %d: %.0f ms (one J/K pass, %s density)' % (len(veff_ms), veff_ms[-1],
           'full' if len(a) < 3 and 'dm_last' not in k else 'difference'), flush=True)
     return out
 
