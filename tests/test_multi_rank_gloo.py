@@ -52,6 +52,12 @@ if rank == 0:
     from oracle import oracle
     rj, rk = oracle.get_jk(mol, dm, hermi=1)
     assert abs(vj.numpy() - rj).max() < 1e-10 and abs(vk.numpy() - rk).max() < 1e-10
+# short-range K (two operator terms in one pass, its own screening lists and launch costs) over 2 ranks
+os.environ['B200_PARTITION'] = 'hybrid'
+ks = jk.get_k(mol, dm, hermi=1, vhfopt=opt, omega=-0.4)      # measuring build of the SR lists
+ks2 = jk.get_k(mol, dm, hermi=1, vhfopt=opt, omega=-0.4)     # partitioned by cost
+ks1 = jk.get_k(mol, dm, hermi=1, vhfopt=opt1, omega=-0.4)
+assert abs(ks - ks1).max() < 1e-11 and abs(ks2 - ks1).max() < 1e-11
 # every rank must hold the full result
 t = torch.stack([vj.abs().sum(), vk.abs().sum()])
 ts = [torch.zeros_like(t) for _ in range(2)]
