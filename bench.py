@@ -133,14 +133,21 @@ def metric_name(args):
     return 'J/K build s/iter (direct SCF, %s %s)' % (args.mol, args.basis)
 
 
-def workload_config(mol_name, basis, world, extra=None):
-    """`config` of the JSON line -- identical keys and workload string for both arms."""
-    cfg = {'workload': '%s RHF/%s direct-SCF J/K build (hermi=1, n_dm=1, direct_scf_tol=1e-13)' % (mol_name, basis),
-           'density': 'synthetic symmetric, exp(-0.8 R_AB/Bohr) decay + identity (fixed seed; no SCF driver in the '
-                      'product scope, the test-side RHF loop of tests/scf_driver.py covers converged densities)',
-           'n_gpus': world}
-    cfg.update(extra or {})
-    return cfg
+def workload_config(mol_name, basis, world, mol=None):
+    """`config` of the JSON line -- the same keys and values for both arms (built from the molecule alone)."""
+    from gpu4pyscf_b200.gto.mole import SortedGTO
+    mol = load_mol(mol_name, basis) if mol is None else mol
+    smol = SortedGTO.from_mol(mol)
+    return {'workload': '%s RHF/%s direct-SCF J/K build (hermi=1, n_dm=1, direct_scf_tol=1e-13)' % (mol_name, basis),
+            'density': 'synthetic symmetric, exp(-0.8 R_AB/Bohr) decay + identity (fixed seed; no SCF driver in the '
+                       'product scope, the test-side RHF loop of tests/scf_driver.py covers converged densities)',
+            'n_gpus': world,
+            'nao': mol.nao, 'nao_sorted_cart': smol.nao, 'nbas_sorted': smol.nbas,
+            'parallelism': 'light class launches whole on one rank (by measured cost), work items (X pair, Y chunk / '
+                           'row block) of the heavy launches dealt round-robin over %d rank(s), one all-reduce of [J|K]'
+                           % world,
+            'l2': 'inputs+outputs (D,J,K = %.0f MB) exceed L2; kernels are FP64-compute bound'
+                  % (3 * smol.nao * smol.nao * 8 / 1e6)}
 
 
 def committed_counters(mol_name, basis):
@@ -420,12 +427,7 @@ def main():
             'metric': metric_name(args), 'value': ms_step * 1e-3, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': False,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args.mol, args.basis, world, {
-                'nao': nao, 'nao_sorted_cart': nao_s, 'nbas_sorted': opt.sorted_mol.nbas,
-                'parallelism': 'work items (X pair, Y chunk / row block) of every class launch dealt round-robin '
-                               'over %d rank(s), one all-reduce of [J|K]' % world,
-                'l2': 'inputs+outputs (D,J,K = %.0f MB) exceed L2; kernels are FP64-compute bound'
-                      % (3 * nao_s * nao_s * 8 / 1e6)}),
+            'config': workload_config(args.mol, args.basis, world, mol),
             'tflops_fp64': achieved,
             'f_alg': f_alg_total,
             'f_hw': f_hw,
